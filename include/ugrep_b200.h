@@ -1,0 +1,172 @@
+/*
+ * ugrep_b200.h — C ABI of the B200-native buffer-scan path for ugrep.
+ *
+ * This is the drop-in boundary.  The reference has no C plugin
+ * ABI; its boundary is the C++ pair reflex::Pattern / reflex::Matcher.  The
+ * functions below are what a patched reflex::Matcher binds (see
+ * INTEGRATION.md): the compiled pattern tables go in once, a buffer goes in per
+ * file, and counts / (line, offset, length, accept) records come back.
+ *
+ * Everything is plain pointers and sizes.  There is NO CPU fallback: every scan
+ * entry point runs sm_100a CUDA kernels or returns a non-zero status.
+ *
+ * Reference interfaces replaced (all paths into /root/reference):
+ *   ugx_pattern_create    reflex::Pattern tables as consumed by reflex::Matcher
+ *                         (include/reflex/pattern.h:1288-1334; the (code, pred)
+ *                         constructor pattern.h:151-159, loader lib/pattern.cpp:199-274)
+ *   ugx_count_lines       `ugrep -c`    loop, src/ugrep.cpp:10567-10586  (find + skip('\n'))
+ *   ugx_count_matches     `ugrep -c -o` loop, src/ugrep.cpp:10536-10566  (find)
+ *   ugx_find_all          `ugrep -o [-n -b]` loop, src/ugrep.cpp:10857-11047 and the
+ *                         state Output::header reads (lineno(), first(), begin(), size();
+ *                         include/reflex/absmatcher.h:695-766, :901-905)
+ *   ugx_count_newlines    reflex::nlcount, lib/simd.cpp:62-166
+ * each of which is a loop over reflex::Matcher::match(FIND), lib/matcher.cpp:42-750,
+ * with the prefilters of lib/matcher.cpp:797-3549 / lib/matcher_avx2.cpp.
+ */
+#ifndef UGREP_B200_H
+#define UGREP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UGX_ABI_VERSION 1
+
+/* status codes (0 = ok; nothing ever falls back to the CPU) */
+enum {
+  UGX_OK            = 0,
+  UGX_E_INVALID     = 1, /* bad argument / malformed pattern tables */
+  UGX_E_UNSUPPORTED = 2, /* pattern uses a feature outside the path's scope (HEAD/TAIL lookahead, REDO, '\n' transitions, ...) */
+  UGX_E_CUDA        = 3, /* CUDA runtime error, see ugx_last_error() */
+  UGX_E_NOMEM       = 4, /* host or device allocation failed */
+  UGX_E_OVERFLOW    = 5, /* caller's record buffer too small: *n_out holds the required count */
+  UGX_E_IO          = 6  /* pattern file unreadable */
+};
+
+/* reflex::Matcher option letters (include/reflex/absmatcher.h:354-388) */
+#define UGX_OPT_N 0x01u /* "N": accept empty matches (ugrep -Y) */
+#define UGX_OPT_W 0x02u /* "W": whole-word matching (ugrep -w) */
+
+#define UGX_BTAP 2048 /* reflex::Pattern::Const::BTAP */
+#define UGX_HASH 4096 /* reflex::Pattern::Const::HASH */
+
+/*
+ * The prefilter block of a compiled reflex::Pattern: a field-for-field image of
+ * the members reflex::Matcher reads (include/reflex/pattern.h:1305-1334).
+ * bit/tap/pma/pmh hold the in-memory values (a 0 bit = "may match").
+ */
+typedef struct ugx_prefilter {
+  uint32_t len;  /* len_: length of the literal prefix in chr[] (0 = none) */
+  uint32_t min;  /* min_: minimum length of what follows the prefix, 0..8 */
+  uint32_t pin;  /* pin_: number of needle bytes per needle position, 0..16 */
+  uint32_t lcp;  /* lcp_: primary needle position */
+  uint32_t lcs;  /* lcs_: secondary needle position */
+  uint32_t bmd;  /* bmd_: Boyer-Moore distance (>0 selects the B-M routines) */
+  uint32_t npy;  /* npy_: bitap entropy */
+  uint32_t one;  /* one_: pattern is the single literal chr[0..len) */
+  uint32_t bol;  /* bol_: every alternative is anchored with ^ */
+  uint32_t lbk;  /* lbk_: look-back distance, 0xffff = unbounded, 0 = none */
+  uint32_t lbm;  /* lbm_: minimum look-back distance */
+  uint32_t cut;  /* cut_: DFA s-t cut depth (informational) */
+  uint8_t  chr[256];      /* chr_: literal prefix, or 2*pin needle bytes */
+  uint8_t  bit[256];      /* bit_ */
+  uint8_t  tap[UGX_BTAP]; /* tap_: bitap hashed byte pairs */
+  uint8_t  pma[UGX_HASH]; /* pma_: PM4 predictor (min < 4) */
+  uint8_t  pmh[UGX_HASH]; /* pmh_: hashed Bloom predictor (min >= 4) */
+  uint8_t  cbk[32];       /* cbk_ as a 256-bit little-endian bitset */
+  uint8_t  fst[32];       /* fst_ as a 256-bit little-endian bitset */
+  uint8_t  bms[256];      /* bms_: Boyer-Moore shifts */
+} ugx_prefilter;
+
+/* UGXP container: header, ugx_prefilter, nop opcode words, regex text (informational) */
+#define UGX_FILE_MAGIC "UGXP\1\0\0\0"
+typedef struct ugx_file_header {
+  char     magic[8];
+  uint32_t nop;            /* number of 32-bit opcode words */
+  uint32_t regex_len;      /* bytes of regex text after the opcode words */
+  uint32_t prefilter_size; /* sizeof(ugx_prefilter) at write time */
+  uint32_t matcher_flags;  /* UGX_OPT_* the pattern was meant to be used with */
+} ugx_file_header;
+
+/* one match, in input order: what lineno()/first()/size()/accept() return for it */
+typedef struct ugx_match {
+  uint64_t line;   /* 1-based line number of the match start (+ base_line) */
+  uint64_t offset; /* 0-based byte offset of the match start (+ base_offset) */
+  uint32_t len;    /* length in bytes */
+  uint32_t cap;    /* accept index: 1-based alternative number */
+} ugx_match;
+
+/* facts about an uploaded pattern */
+typedef struct ugx_pattern_info {
+  uint32_t nop;          /* opcode words */
+  uint32_t states;       /* reachable DFA states after flattening */
+  uint32_t classes;      /* byte equivalence classes */
+  uint32_t table_bytes;  /* dense transition table size */
+  uint32_t table_in_smem;/* 1 if the scan kernels stage the table in shared memory */
+  uint32_t advance;      /* UGX_ADV_* prefilter routine selected (init_advance, lib/matcher.cpp:797-954) */
+  uint32_t has_meta;     /* DFA has META (anchor / word boundary) edges */
+  uint32_t lookback;     /* lbk != 0 */
+} ugx_pattern_info;
+
+/* prefilter routine families of Matcher::init_advance (lib/matcher.cpp:797-954) */
+enum {
+  UGX_ADV_NONE = 0,
+  UGX_ADV_PIN1_ONE, UGX_ADV_PIN1_PMA, UGX_ADV_PIN1_PMH,
+  UGX_ADV_PIN_ONE,  UGX_ADV_PIN_PMA,  UGX_ADV_PIN_PMH,
+  UGX_ADV_MIN1, UGX_ADV_MIN2, UGX_ADV_MIN3, UGX_ADV_MIN4, UGX_ADV_PMA,
+  UGX_ADV_CHAR, UGX_ADV_CHAR_PMA, UGX_ADV_CHAR_PMH,
+  UGX_ADV_STRING, UGX_ADV_STRING_PMA, UGX_ADV_STRING_PMH
+};
+
+typedef struct ugx_pattern ugx_pattern; /* immutable once created; shareable between host threads */
+typedef struct ugx_scanner ugx_scanner; /* per host thread / per stream scratch (counters, record arena) */
+
+/* totals every scan reports */
+typedef struct ugx_totals {
+  uint64_t matches;        /* count-lines: matching lines; otherwise: matches */
+  uint64_t newlines;       /* '\n' bytes in the buffer (line-number base for the next shard) */
+  uint64_t long_lines;     /* lines that took the long-line path */
+  float    kernel_ms;      /* device time of the scan kernels (CUDA events on the scan stream) */
+  uint32_t launches;       /* kernels launched by this call */
+} ugx_totals;
+
+const char *ugx_last_error(void);
+int  ugx_abi_version(void);
+
+/* pattern: flatten the opcode table to a dense class-compressed DFA and upload it with the prefilter tables */
+int  ugx_pattern_create(const uint32_t *opc, uint32_t nop, const ugx_prefilter *pf,
+                        uint32_t matcher_flags, int device, ugx_pattern **out);
+int  ugx_pattern_load(const char *path, int device, ugx_pattern **out);
+int  ugx_pattern_info_get(const ugx_pattern *p, ugx_pattern_info *info);
+void ugx_pattern_destroy(ugx_pattern *p);
+
+/* scanner: owns a stream-ordered scratch arena on `device`; `stream` is a cudaStream_t (NULL = default stream) */
+int  ugx_scanner_create(int device, void *stream, ugx_scanner **out);
+void ugx_scanner_destroy(ugx_scanner *s);
+
+/*
+ * Scans.  `buf` is nbytes of text; it may be a device pointer (scanned in place)
+ * or a host pointer (staged to the device inside the call, chunked and
+ * overlapped with the scan).  The buffer is one file or one line-aligned shard.
+ */
+int  ugx_count_lines(ugx_scanner *s, const ugx_pattern *p, const void *buf, uint64_t nbytes,
+                     ugx_totals *totals);
+int  ugx_count_matches(ugx_scanner *s, const ugx_pattern *p, const void *buf, uint64_t nbytes,
+                       ugx_totals *totals);
+/* records are written to the host array `out` (capacity `cap`), in input order */
+int  ugx_find_all(ugx_scanner *s, const ugx_pattern *p, const void *buf, uint64_t nbytes,
+                  uint64_t base_offset, uint64_t base_line,
+                  ugx_match *out, uint64_t cap, uint64_t *n_out, ugx_totals *totals);
+/* records stay on the device: *dev_out is owned by the scanner and valid until its next call */
+int  ugx_find_all_device(ugx_scanner *s, const ugx_pattern *p, const void *buf, uint64_t nbytes,
+                         uint64_t base_offset, uint64_t base_line,
+                         const ugx_match **dev_out, uint64_t *n_out, ugx_totals *totals);
+int  ugx_count_newlines(ugx_scanner *s, const void *buf, uint64_t nbytes, ugx_totals *totals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UGREP_B200_H */
