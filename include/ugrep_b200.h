@@ -164,6 +164,8 @@ int  ugx_find_all(ugx_scanner *s, const ugx_pattern *p, const void *buf, uint64_
 int  ugx_find_all_device(ugx_scanner *s, const ugx_pattern *p, const void *buf, uint64_t nbytes,
                          uint64_t base_offset, uint64_t base_line,
                          const ugx_match **dev_out, uint64_t *n_out, ugx_totals *totals);
+/* copy `count` records of the last ugx_find_all_device result, starting at record `first`, to the host */
+int  ugx_scanner_fetch(ugx_scanner *s, ugx_match *out, uint64_t first, uint64_t count);
 int  ugx_count_newlines(ugx_scanner *s, const void *buf, uint64_t nbytes, ugx_totals *totals);
 
 #ifdef __cplusplus

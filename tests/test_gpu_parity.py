@@ -1,0 +1,143 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the
+oracle (oracle/oracle.c) on the same seeded inputs; against the unmodified
+reference (oracle/_ref/ugrep, refscan) where it travelled with the snapshot."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from ugrep_b200 import corpus
+
+pytestmark = pytest.mark.gpu
+
+PAT_DIR = os.path.join(O.ROOT, "ugrep_b200", "patterns")
+# config -> (pattern file, corpus, mode)
+CONFIGS = {
+    "c1": ("c1", "c1", "lines"),
+    "c2": ("c2", "c2", "lines"),
+    "c3": ("c3", "c3", "list"),
+    "c3b": ("c3b", "c3", "list"),
+    "c3c": ("c3c", "c3", "list"),
+    "c4": ("c4", "c4", "lines"),
+    "c5": ("c5", "c5", "matches"),
+}
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the -m gpu tests must run on the B200 box")
+    from ugrep_b200 import api
+    return api, api.Scanner(0)
+
+
+def run_mode(api, sc, pat, data, mode):
+    if mode == "lines":
+        return sc.count_lines(pat, data).matches
+    if mode == "matches":
+        return sc.count_matches(pat, data).matches
+    rec, tot = sc.find_all(pat, data)
+    assert tot.matches == len(rec)
+    return rec
+
+
+def oracle_mode(op, data, mode):
+    if mode == "lines":
+        return op.count_lines(data)
+    if mode == "matches":
+        return op.count_matches(data)
+    return op.find_all(data)
+
+
+def same(a, b):
+    if isinstance(a, np.ndarray):
+        return len(a) == len(b) and bool(np.all(a == b))
+    return a == b
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+@pytest.mark.parametrize("mode_override", [None, "lines", "matches", "list"])
+def test_config_vs_oracle(gpu, name, mode_override):
+    api, sc = gpu
+    pfile, cname, mode = CONFIGS[name]
+    mode = mode_override or mode
+    path = os.path.join(PAT_DIR, pfile + ".ugxp")
+    pat = api.Pattern.load(path, 0)
+    op = O.OraclePattern(path)
+    data = corpus.block(cname, 3 << 20)
+    got = run_mode(api, sc, pat, data, mode)
+    want = oracle_mode(op, data, mode)
+    assert same(got, want), "%s/%s: cuda %r oracle %r" % (name, mode, got if not isinstance(got, np.ndarray) else len(got),
+                                                        want if not isinstance(want, np.ndarray) else len(want))
+    # device-resident input gives the same answer as the host-staged one
+    import torch
+    dev = torch.from_numpy(data).cuda()
+    got2 = run_mode(api, sc, pat, dev, mode)
+    assert same(got2, want)
+    if mode == "list":
+        assert sc.count_matches(pat, dev).newlines == O.newlines(data)
+
+
+EDGE_INPUTS = [
+    b"",
+    b"\n",
+    b"\n\n\n",
+    b"Sherlock Holmes",
+    b"Sherlock Holmes\n",
+    b"xSherlock HolmesSherlock Holmes Sherlock Holme\nSherlock Holmes",
+    b"Running\nWalking and Thinking\n\nmorning Singing",
+    b"a" * 70000 + b" Running " + b"b" * 70000 + b"\n" + b"Walking",
+    b"2026-01-02T03:04:05 ERROR svc01 call 555-1234 ext 123-4567 id=1\n" * 3 + b"WARN 111-2222",
+    "naïve Ωmega αβγ NAÏVE\nκόσμος\n".encode("utf-8"),
+    b"\r\nWalking\r\n",
+]
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_edge_inputs(gpu, name):
+    api, sc = gpu
+    pfile, _, _ = CONFIGS[name]
+    path = os.path.join(PAT_DIR, pfile + ".ugxp")
+    pat = api.Pattern.load(path, 0)
+    op = O.OraclePattern(path)
+    for data in EDGE_INPUTS:
+        for mode in ("lines", "matches", "list"):
+            got = run_mode(api, sc, pat, data, mode)
+            want = oracle_mode(op, data, mode)
+            assert same(got, want), "%s/%s on %r" % (name, mode, data[:60])
+
+
+def test_ragged_sizes(gpu):
+    """every buffer length around the strip / tile boundaries"""
+    api, sc = gpu
+    path = os.path.join(PAT_DIR, "c5.ugxp")
+    pat = api.Pattern.load(path, 0)
+    op = O.OraclePattern(path)
+    base = corpus.block("c5", 40000)
+    for n in list(range(0, 200)) + [16383, 16384, 16385, 32767, 32768, 32769, len(base)]:
+        data = base[:n]
+        assert sc.count_matches(pat, data).matches == op.count_matches(data), n
+        assert sc.count_lines(pat, data).matches == op.count_lines(data), n
+
+
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref (the built reference) did not travel")
+@pytest.mark.parametrize("name,cli", [
+    ("c1", ["-c", "-F", "Sherlock Holmes"]),
+    ("c3", ["-n", "-b", "-o", "[A-Z][a-z]+ing\\b"]),
+    ("c3b", ["-n", "-b", "-o", "[A-Z][a-z]+ing"]),
+    ("c3c", ["-n", "-b", "-o", "[A-Z][a-z]{1,9}ing\\b"]),
+    ("c4", ["-i", "-c", "\\p{Greek}+|naïve\\w*"]),
+    ("c5", ["-c", "-o", "-e", "ERROR|WARN", "-e", "\\d{3}-\\d{4}"]),
+])
+def test_config_vs_reference_cli(gpu, name, cli):
+    """bit-exact against the reference's own output on the same input"""
+    api, sc = gpu
+    pfile, cname, mode = CONFIGS[name]
+    pat = api.Pattern.load(os.path.join(PAT_DIR, pfile + ".ugxp"), 0)
+    data = corpus.block(cname, 2 << 20)
+    rc, ref = O.ref_cli(cli, data)
+    got = run_mode(api, sc, pat, data, mode)
+    mine = O.format_list(data, got) if mode == "list" else b"%d\n" % got
+    assert mine == ref

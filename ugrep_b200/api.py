@@ -1,0 +1,188 @@
+"""ctypes binding of the C ABI (include/ugrep_b200.h) — the call a Python user makes.
+
+The host-side mirror of the reference interface: ``Pattern`` stands for a compiled
+``reflex::Pattern`` (opcode words + prefilter fields), ``Scanner`` for one
+``reflex::Matcher`` bound to a device stream; ``count_lines`` / ``count_matches`` /
+``find_all`` are the three ``Grep::search`` loops of the configs
+(/root/reference/src/ugrep.cpp:10567-10586, :10536-10566, :10857-11047).
+
+There is no CPU fallback: if ``libugrep_b200.so`` is missing or no CUDA device is
+usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libugrep_b200.so")
+
+MATCH_DTYPE = np.dtype([("line", "<u8"), ("offset", "<u8"), ("len", "<u4"), ("cap", "<u4")])
+
+ADVANCE_NAMES = ["none", "pin1_one", "pin1_pma", "pin1_pmh", "pin_one", "pin_pma", "pin_pmh", "min1", "min2", "min3",
+                 "min4", "pma", "char", "char_pma", "char_pmh", "string", "string_pma", "string_pmh"]
+
+EXPORTS = ["ugx_last_error", "ugx_abi_version", "ugx_pattern_create", "ugx_pattern_load", "ugx_pattern_info_get",
+           "ugx_pattern_destroy", "ugx_scanner_create", "ugx_scanner_destroy", "ugx_count_lines", "ugx_count_matches",
+           "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_count_newlines"]
+
+
+class UgxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("ugx error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _Totals(C.Structure):
+    _fields_ = [("matches", C.c_uint64), ("newlines", C.c_uint64), ("long_lines", C.c_uint64),
+                ("kernel_ms", C.c_float), ("launches", C.c_uint32)]
+
+
+class _Info(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("nop", "states", "classes", "table_bytes", "table_in_smem", "advance",
+                                          "has_meta", "lookback")]
+
+
+@dataclass
+class Totals:
+    matches: int
+    newlines: int
+    long_lines: int
+    kernel_ms: float
+    launches: int
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raises if it has not been built (python -m ugrep_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UgxError(-1, "%s is missing: build it with `python -m ugrep_b200.build` (CUDA only, no CPU fallback)"
+                           % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.ugx_last_error.restype = C.c_char_p
+        L.ugx_pattern_create.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+        L.ugx_pattern_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.ugx_pattern_info_get.argtypes = [C.c_void_p, C.POINTER(_Info)]
+        L.ugx_pattern_destroy.argtypes = [C.c_void_p]
+        L.ugx_pattern_destroy.restype = None
+        L.ugx_scanner_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ugx_scanner_destroy.argtypes = [C.c_void_p]
+        L.ugx_scanner_destroy.restype = None
+        L.ugx_count_lines.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_Totals)]
+        L.ugx_count_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_Totals)]
+        L.ugx_count_newlines.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_Totals)]
+        L.ugx_find_all.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                   C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(_Totals)]
+        L.ugx_find_all_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(_Totals)]
+        L.ugx_scanner_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise UgxError(rc, lib().ugx_last_error().decode("utf-8", "replace"))
+
+
+def _buffer(data):
+    """(pointer, nbytes, keepalive) for a CUDA tensor, numpy array or bytes-like."""
+    if hasattr(data, "data_ptr") and hasattr(data, "is_cuda"):
+        if data.dtype.itemsize != 1:
+            raise TypeError("expected a uint8/int8 tensor")
+        if not data.is_contiguous():
+            data = data.contiguous()
+        return data.data_ptr(), data.numel(), data
+    if isinstance(data, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(data, dtype=np.uint8)
+    else:
+        a = np.ascontiguousarray(data, dtype=np.uint8)
+    return a.ctypes.data, a.size, a
+
+
+class Pattern:
+    """A compiled pattern uploaded to one device (immutable, shareable)."""
+
+    def __init__(self, handle, device: int):
+        self._h = handle
+        self.device = device
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "Pattern":
+        h = C.c_void_p()
+        _check(lib().ugx_pattern_load(os.fsencode(path), device, C.byref(h)))
+        return cls(h, device)
+
+    @property
+    def info(self) -> dict:
+        i = _Info()
+        _check(lib().ugx_pattern_info_get(self._h, C.byref(i)))
+        d = {n: getattr(i, n) for n, _ in _Info._fields_}
+        d["advance_name"] = ADVANCE_NAMES[d["advance"]] if d["advance"] < len(ADVANCE_NAMES) else "?"
+        return d
+
+    def close(self):
+        if self._h:
+            lib().ugx_pattern_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scanner:
+    """Per-thread / per-stream scan context (the Matcher side of the boundary)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._h = C.c_void_p()
+        self.device = device
+        _check(lib().ugx_scanner_create(device, C.c_void_p(stream or 0), C.byref(self._h)))
+
+    def _totals(self, t: _Totals) -> Totals:
+        return Totals(t.matches, t.newlines, t.long_lines, t.kernel_ms, t.launches)
+
+    def count_lines(self, pattern: Pattern, data) -> Totals:
+        ptr, n, keep = _buffer(data)
+        t = _Totals()
+        _check(lib().ugx_count_lines(self._h, pattern._h, C.c_void_p(ptr), n, C.byref(t)))
+        return self._totals(t)
+
+    def count_matches(self, pattern: Pattern, data) -> Totals:
+        ptr, n, keep = _buffer(data)
+        t = _Totals()
+        _check(lib().ugx_count_matches(self._h, pattern._h, C.c_void_p(ptr), n, C.byref(t)))
+        return self._totals(t)
+
+    def find_all(self, pattern: Pattern, data, base_offset: int = 0, base_line: int = 0):
+        """All matches in input order as a structured array (line, offset, len, cap) + totals."""
+        ptr, n, keep = _buffer(data)
+        t = _Totals()
+        dev = C.c_void_p()
+        cnt = C.c_uint64()
+        _check(lib().ugx_find_all_device(self._h, pattern._h, C.c_void_p(ptr), n, base_offset, base_line,
+                                         C.byref(dev), C.byref(cnt), C.byref(t)))
+        out = np.zeros(cnt.value, dtype=MATCH_DTYPE)
+        if cnt.value:
+            _check(lib().ugx_scanner_fetch(self._h, out.ctypes.data, 0, cnt.value))
+        return out, self._totals(t)
+
+    def close(self):
+        if self._h:
+            lib().ugx_scanner_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,512 @@
+// capi.cu — the C ABI declared in include/ugrep_b200.h: pattern upload, scanner scratch,
+// and the scan entry points.  Host C++ only calls CUDA through this file and scan_kernels.cu.
+// There is no CPU scan path: without a usable CUDA device every entry point fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/ugrep_b200.h"
+#include "device_pattern.cuh"
+#include "pattern_host.hpp"
+#include "scan_kernels.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+  g_err = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return UGX_E_CUDA;
+}
+
+#define CU(call)                         \
+  do                                     \
+  {                                      \
+    cudaError_t e_ = (call);             \
+    if (e_ != cudaSuccess)               \
+      return cuda_fail(e_, #call);       \
+  } while (0)
+
+const int k_word_ranges[] = {
+#include "word_ranges.inc"
+};
+
+template <typename T>
+int upload(T*& dev, const void* host, size_t bytes)
+{
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+  if (e != cudaSuccess)
+    return cuda_fail(e, "cudaMalloc");
+  if (bytes)
+  {
+    e = cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess)
+    {
+      cudaFree(p);
+      return cuda_fail(e, "cudaMemcpy");
+    }
+  }
+  dev = static_cast<T*>(p);
+  return UGX_OK;
+}
+
+void set256(uint32_t* set, const uint8_t* bytes32)
+{
+  for (int i = 0; i < 8; ++i)
+    set[i] = static_cast<uint32_t>(bytes32[4 * i]) | (static_cast<uint32_t>(bytes32[4 * i + 1]) << 8) |
+             (static_cast<uint32_t>(bytes32[4 * i + 2]) << 16) | (static_cast<uint32_t>(bytes32[4 * i + 3]) << 24);
+}
+
+} // namespace
+
+struct ugx_pattern {
+  ugx::HostDfa dfa;
+  ugx_prefilter pf;
+  uint32_t flags = 0;
+  int adv = 0;
+  int device = 0;
+  uint32_t nop = 0;
+  ugx::DevPattern dev;
+  std::vector<void*> allocs;
+  ~ugx_pattern()
+  {
+    for (void* p : allocs)
+      cudaFree(p);
+  }
+};
+
+struct ugx_scanner {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // scratch
+  uint64_t* tile_matches = nullptr;
+  uint64_t* tile_newlines = nullptr;
+  uint64_t tiles_cap = 0;
+  uint32_t* strip_counts = nullptr;
+  uint64_t strips_cap = 0;
+  unsigned long long* totals = nullptr; // device [4]
+  unsigned long long* h_totals = nullptr; // pinned [4]
+  ugx_match* records = nullptr;
+  uint64_t records_cap = 0;
+  uint64_t records_n = 0;
+  uint8_t* stage = nullptr; // device copy of a host buffer
+  uint64_t stage_cap = 0;
+};
+
+extern "C" {
+
+const char* ugx_last_error(void) { return g_err.c_str(); }
+int ugx_abi_version(void) { return UGX_ABI_VERSION; }
+
+int ugx_pattern_create(const uint32_t* opc, uint32_t nop, const ugx_prefilter* pf, uint32_t matcher_flags, int device,
+                       ugx_pattern** out)
+{
+  if (opc == nullptr || nop == 0 || pf == nullptr || out == nullptr)
+    return fail(UGX_E_INVALID, "ugx_pattern_create: null argument");
+  ugx_pattern* p = new (std::nothrow) ugx_pattern();
+  if (p == nullptr)
+    return fail(UGX_E_NOMEM, "out of host memory");
+  std::string err;
+  int rc = ugx::flatten_dfa(opc, nop, p->dfa, err);
+  if (rc == UGX_OK)
+    rc = ugx::check_scope(p->dfa, *pf, matcher_flags, err);
+  if (rc != UGX_OK)
+  {
+    delete p;
+    return fail(rc, err);
+  }
+  p->pf = *pf;
+  p->flags = matcher_flags;
+  p->adv = ugx::select_advance(*pf, matcher_flags);
+  p->device = device;
+  p->nop = nop;
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess)
+  {
+    delete p;
+    return cuda_fail(ce, "cudaSetDevice (the scan path needs a CUDA device; there is no CPU fallback)");
+  }
+  ugx::DevPattern& d = p->dev;
+  memset(&d, 0, sizeof(d));
+  d.adv = p->adv;
+  d.len = pf->len;
+  d.min = pf->min;
+  d.pin = pf->pin;
+  d.lcp = pf->lcp;
+  d.lcs = pf->lcs;
+  d.one = pf->one;
+  d.bol = pf->bol;
+  d.lbk = pf->lbk;
+  d.lbm = pf->lbm;
+  d.flags = matcher_flags;
+  d.nstates = p->dfa.nstates;
+  d.ncls = p->dfa.ncls;
+  d.has_meta = p->dfa.has_meta;
+  d.to_start = p->dfa.to_start;
+  d.nop = nop;
+  d.table_bytes = p->dfa.table_bytes();
+  d.n_word_ranges = sizeof(k_word_ranges) / sizeof(int) / 2;
+  memcpy(d.chr, pf->chr, 256);
+  set256(d.cbk, pf->cbk);
+  set256(d.fst, pf->fst);
+  if (pf->len == 0 && pf->pin >= 1 && pf->pin <= 16)
+  {
+    for (uint32_t i = 0; i < pf->pin; ++i)
+    {
+      uint32_t a = pf->chr[i], b = pf->chr[pf->pin + i];
+      d.pin_a[a >> 5] |= 1u << (a & 31);
+      d.pin_b[b >> 5] |= 1u << (b & 31);
+    }
+  }
+  // accept words: bit 31 marks a state without outgoing byte edges (the interpreter halts there before reading)
+  std::vector<uint32_t> acc(p->dfa.nstates);
+  for (uint32_t s = 0; s < p->dfa.nstates; ++s)
+  {
+    bool any = false;
+    for (uint32_t c = 0; c < p->dfa.ncls && !any; ++c)
+      any = p->dfa.next[static_cast<size_t>(s) * p->dfa.ncls + c] != ugx::DEAD;
+    acc[s] = (p->dfa.accept[s] & 0x7fffffffu) | (any ? 0u : 0x80000000u);
+  }
+  std::vector<uint32_t> opcp(opc, opc + nop);
+  opcp.push_back(ugx::OP_HALT);
+  opcp.push_back(ugx::OP_HALT);
+  std::vector<uint16_t> next = p->dfa.next;
+  next.resize((next.size() + 7) / 8 * 8, ugx::DEAD); // whole uint4s for the staging loop
+  uint8_t* d_cls = nullptr;
+  uint16_t* d_next = nullptr;
+  uint32_t* d_acc = nullptr;
+  uint32_t* d_opc = nullptr;
+  uint8_t* d_pred = nullptr;
+  uint8_t* d_tap = nullptr;
+  int* d_words = nullptr;
+  rc = upload(d_cls, p->dfa.cls, 256);
+  if (rc == UGX_OK) { p->allocs.push_back(d_cls); rc = upload(d_next, next.data(), next.size() * 2); }
+  if (rc == UGX_OK) { p->allocs.push_back(d_next); rc = upload(d_acc, acc.data(), acc.size() * 4); }
+  if (rc == UGX_OK) { p->allocs.push_back(d_acc); rc = upload(d_opc, opcp.data(), opcp.size() * 4); }
+  if (rc == UGX_OK) { p->allocs.push_back(d_opc); rc = upload(d_pred, pf->min < 4 ? pf->pma : pf->pmh, UGX_HASH); }
+  if (rc == UGX_OK) { p->allocs.push_back(d_pred); rc = upload(d_tap, pf->tap, UGX_BTAP); }
+  if (rc == UGX_OK) { p->allocs.push_back(d_tap); rc = upload(d_words, k_word_ranges, sizeof(k_word_ranges)); }
+  if (rc == UGX_OK) p->allocs.push_back(d_words);
+  if (rc != UGX_OK)
+  {
+    delete p;
+    return rc;
+  }
+  d.cls = d_cls;
+  d.next = d_next;
+  d.accept = d_acc;
+  d.opc = d_opc;
+  d.pred = d_pred;
+  d.tap = d_tap;
+  d.word_ranges = d_words;
+  *out = p;
+  return UGX_OK;
+}
+
+int ugx_pattern_load(const char* path, int device, ugx_pattern** out)
+{
+  FILE* f = fopen(path, "rb");
+  if (f == nullptr)
+    return fail(UGX_E_IO, std::string("cannot open ") + path);
+  ugx_file_header h;
+  ugx_prefilter pf;
+  std::vector<uint32_t> opc;
+  bool ok = fread(&h, sizeof(h), 1, f) == 1 && memcmp(h.magic, UGX_FILE_MAGIC, 8) == 0 &&
+            h.prefilter_size == sizeof(pf) && fread(&pf, sizeof(pf), 1, f) == 1;
+  if (ok)
+  {
+    opc.resize(h.nop);
+    ok = h.nop > 0 && fread(opc.data(), 4, h.nop, f) == h.nop;
+  }
+  fclose(f);
+  if (!ok)
+    return fail(UGX_E_IO, std::string("not a UGXP pattern file: ") + path);
+  return ugx_pattern_create(opc.data(), h.nop, &pf, h.matcher_flags, device, out);
+}
+
+int ugx_pattern_info_get(const ugx_pattern* p, ugx_pattern_info* info)
+{
+  if (p == nullptr || info == nullptr)
+    return fail(UGX_E_INVALID, "null argument");
+  info->nop = p->nop;
+  info->states = p->dfa.nstates;
+  info->classes = p->dfa.ncls;
+  info->table_bytes = p->dfa.table_bytes();
+  info->table_in_smem = !p->dfa.has_meta && p->dfa.table_bytes() <= ugx::SCAN_MAX_SMEM_TABLE;
+  info->advance = p->adv;
+  info->has_meta = p->dfa.has_meta;
+  info->lookback = p->pf.lbk != 0;
+  return UGX_OK;
+}
+
+void ugx_pattern_destroy(ugx_pattern* p)
+{
+  if (p != nullptr)
+  {
+    cudaSetDevice(p->device);
+    delete p;
+  }
+}
+
+int ugx_scanner_create(int device, void* stream, ugx_scanner** out)
+{
+  if (out == nullptr)
+    return fail(UGX_E_INVALID, "null argument");
+  CU(cudaSetDevice(device));
+  ugx_scanner* s = new (std::nothrow) ugx_scanner();
+  if (s == nullptr)
+    return fail(UGX_E_NOMEM, "out of host memory");
+  s->device = device;
+  s->stream = static_cast<cudaStream_t>(stream);
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e == cudaSuccess)
+    e = cudaEventCreate(&s->ev0);
+  if (e == cudaSuccess)
+    e = cudaEventCreate(&s->ev1);
+  if (e == cudaSuccess)
+    e = cudaMalloc(reinterpret_cast<void**>(&s->totals), 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess)
+    e = cudaMallocHost(reinterpret_cast<void**>(&s->h_totals), 4 * sizeof(unsigned long long));
+  if (e != cudaSuccess)
+  {
+    ugx_scanner_destroy(s);
+    return cuda_fail(e, "ugx_scanner_create");
+  }
+  s->sm_count = prop.multiProcessorCount;
+  *out = s;
+  return UGX_OK;
+}
+
+void ugx_scanner_destroy(ugx_scanner* s)
+{
+  if (s == nullptr)
+    return;
+  cudaSetDevice(s->device);
+  cudaFree(s->tile_matches);
+  cudaFree(s->tile_newlines);
+  cudaFree(s->strip_counts);
+  cudaFree(s->totals);
+  cudaFreeHost(s->h_totals);
+  cudaFree(s->records);
+  cudaFree(s->stage);
+  if (s->ev0)
+    cudaEventDestroy(s->ev0);
+  if (s->ev1)
+    cudaEventDestroy(s->ev1);
+  delete s;
+}
+
+} // extern "C"
+
+namespace {
+
+template <typename T>
+int ensure(T*& ptr, uint64_t& cap, uint64_t need)
+{
+  if (need <= cap)
+    return UGX_OK;
+  if (ptr != nullptr)
+    cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+  uint64_t want = need + need / 8 + 64;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+  if (e != cudaSuccess)
+  {
+    g_err = std::string("cudaMalloc scratch: ") + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? UGX_E_NOMEM : UGX_E_CUDA;
+  }
+  ptr = static_cast<T*>(p);
+  cap = want;
+  return UGX_OK;
+}
+
+// make `buf` visible to the device: device pointers are used in place, host pointers are staged
+int resolve(ugx_scanner* s, const void* buf, uint64_t n, const uint8_t** dev, uint64_t* h2d)
+{
+  *h2d = 0;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, buf);
+  if (e == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged))
+  {
+    *dev = static_cast<const uint8_t*>(buf);
+    return UGX_OK;
+  }
+  if (e != cudaSuccess)
+    cudaGetLastError(); // plain host memory on older drivers reports an error: clear it
+  int rc = ensure(s->stage, s->stage_cap, n + 16);
+  if (rc != UGX_OK)
+    return rc;
+  CU(cudaMemcpyAsync(s->stage, buf, n, cudaMemcpyHostToDevice, s->stream));
+  *dev = s->stage;
+  *h2d = n;
+  return UGX_OK;
+}
+
+int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t n, int mode, bool want_records,
+                uint64_t base_offset, uint64_t base_line, const ugx_match** dev_out, uint64_t* n_out, ugx_totals* totals)
+{
+  if (s == nullptr || p == nullptr || (buf == nullptr && n != 0))
+    return fail(UGX_E_INVALID, "null argument");
+  if (s->device != p->device)
+    return fail(UGX_E_INVALID, "pattern and scanner live on different devices");
+  ugx_totals tt;
+  memset(&tt, 0, sizeof(tt));
+  if (n_out)
+    *n_out = 0;
+  if (dev_out)
+    *dev_out = nullptr;
+  if (n == 0)
+  {
+    if (totals)
+      *totals = tt;
+    return UGX_OK;
+  }
+  CU(cudaSetDevice(s->device));
+  const uint8_t* dbuf = nullptr;
+  uint64_t h2d = 0;
+  int rc = resolve(s, buf, n, &dbuf, &h2d);
+  if (rc != UGX_OK)
+    return rc;
+  const uint64_t ntiles = (n + ugx::SCAN_TILE - 1) / ugx::SCAN_TILE;
+  const uint64_t nstrips = (n + ugx::SCAN_STRIP - 1) / ugx::SCAN_STRIP;
+  uint64_t cap1 = s->tiles_cap, cap2 = s->tiles_cap;
+  rc = ensure(s->tile_matches, cap1, ntiles);
+  if (rc == UGX_OK)
+    rc = ensure(s->tile_newlines, cap2, ntiles);
+  s->tiles_cap = cap1 < cap2 ? cap1 : cap2;
+  if (rc == UGX_OK && want_records)
+    rc = ensure(s->strip_counts, s->strips_cap, nstrips);
+  if (rc != UGX_OK)
+    return rc;
+  ugx::ScanArgs a;
+  a.buf = dbuf;
+  a.n = n;
+  a.ntiles = ntiles;
+  a.tile_matches = s->tile_matches;
+  a.tile_newlines = s->tile_newlines;
+  a.strip_counts = want_records ? s->strip_counts : nullptr;
+  a.out = nullptr;
+  a.out_cap = 0;
+  a.base_offset = base_offset;
+  a.base_line = base_line;
+  CU(cudaEventRecord(s->ev0, s->stream));
+  CU(ugx::launch_scan_lines(p->dev, a, mode, false, s->sm_count, s->stream));
+  CU(ugx::launch_tile_prefix(s->tile_matches, s->tile_newlines, ntiles, s->totals, s->stream));
+  tt.launches = 2;
+  CU(cudaMemcpyAsync(s->h_totals, s->totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+  if (want_records)
+  {
+    CU(cudaStreamSynchronize(s->stream));
+    const uint64_t nrec = s->h_totals[0];
+    rc = ensure(s->records, s->records_cap, nrec);
+    if (rc != UGX_OK)
+      return rc;
+    if (nrec > 0)
+    {
+      a.out = s->records;
+      a.out_cap = nrec;
+      CU(ugx::launch_scan_lines(p->dev, a, mode, true, s->sm_count, s->stream));
+      tt.launches += 1;
+    }
+    s->records_n = nrec;
+    if (n_out)
+      *n_out = nrec;
+    if (dev_out)
+      *dev_out = s->records;
+  }
+  CU(cudaEventRecord(s->ev1, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+  tt.matches = s->h_totals[0];
+  tt.newlines = s->h_totals[1];
+  tt.kernel_ms = ms;
+  if (totals)
+    *totals = tt;
+  return UGX_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int ugx_count_lines(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t nbytes, ugx_totals* totals)
+{
+  return scan_common(s, p, buf, nbytes, 0, false, 0, 0, nullptr, nullptr, totals);
+}
+
+int ugx_count_matches(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t nbytes, ugx_totals* totals)
+{
+  return scan_common(s, p, buf, nbytes, 1, false, 0, 0, nullptr, nullptr, totals);
+}
+
+int ugx_find_all_device(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t nbytes, uint64_t base_offset,
+                        uint64_t base_line, const ugx_match** dev_out, uint64_t* n_out, ugx_totals* totals)
+{
+  return scan_common(s, p, buf, nbytes, 1, true, base_offset, base_line, dev_out, n_out, totals);
+}
+
+int ugx_find_all(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t nbytes, uint64_t base_offset,
+                 uint64_t base_line, ugx_match* out, uint64_t cap, uint64_t* n_out, ugx_totals* totals)
+{
+  const ugx_match* dev = nullptr;
+  uint64_t n = 0;
+  int rc = scan_common(s, p, buf, nbytes, 1, true, base_offset, base_line, &dev, &n, totals);
+  if (rc != UGX_OK)
+    return rc;
+  if (n_out)
+    *n_out = n;
+  if (n > cap)
+    return fail(UGX_E_OVERFLOW, "record buffer too small");
+  if (n > 0)
+  {
+    if (out == nullptr)
+      return fail(UGX_E_INVALID, "null record buffer");
+    CU(cudaMemcpyAsync(out, dev, n * sizeof(ugx_match), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+  }
+  return UGX_OK;
+}
+
+int ugx_scanner_fetch(ugx_scanner* s, ugx_match* out, uint64_t first, uint64_t count)
+{
+  if (s == nullptr || (out == nullptr && count != 0))
+    return fail(UGX_E_INVALID, "null argument");
+  if (first + count > s->records_n)
+    return fail(UGX_E_INVALID, "record range outside the last result");
+  if (count == 0)
+    return UGX_OK;
+  CU(cudaSetDevice(s->device));
+  CU(cudaMemcpyAsync(out, s->records + first, count * sizeof(ugx_match), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return UGX_OK;
+}
+
+int ugx_count_newlines(ugx_scanner* s, const void* buf, uint64_t nbytes, ugx_totals* totals)
+{
+  (void)s;
+  (void)buf;
+  (void)nbytes;
+  (void)totals;
+  return fail(UGX_E_UNSUPPORTED, "ugx_count_newlines: not built yet");
+}
+
+} // extern "C"

@@ -1,0 +1,273 @@
+// pattern_host.cpp — DFA export (host).  See pattern_host.hpp.
+//
+// Input format: the opcode words reflex::Pattern::encode_dfa writes
+// (/root/reference/lib/pattern.cpp:2823-3063; codec include/reflex/pattern.h:1155-1247):
+//   state := [TAKE] META* GOTO+      (state id = index of its first word)
+//   GOTO  := lo<<24 | hi<<16 | idx16 (idx 0xFFFF = HALT, 0xFFFE = LONG: next word 0xFF<<24 | idx24)
+//   META  := (meta-0x100)<<24 | idx16, same LONG rule
+//   TAKE  := 0xFE<<24 | accept24
+// A byte is resolved by first match over the GOTO list, exactly as the interpreter's
+// range search does (lib/matcher.cpp:467-502).
+#include "pattern_host.hpp"
+
+#include <cstring>
+#include <map>
+#include <queue>
+
+namespace ugx {
+
+int select_advance(const ugx_prefilter& pf, uint32_t matcher_flags)
+{
+  if (pf.len == 0)
+  {
+    if (pf.min == 0 && (matcher_flags & UGX_OPT_N))
+      return UGX_ADV_NONE;
+    if (pf.pin == 1)
+      return pf.min < 2 ? UGX_ADV_PIN1_ONE : pf.min < 4 ? UGX_ADV_PIN1_PMA : UGX_ADV_PIN1_PMH;
+    if ((pf.pin >= 2 && pf.pin <= 8) || pf.pin == 16)
+      return pf.min < 2 ? UGX_ADV_PIN_ONE : pf.min < 4 ? UGX_ADV_PIN_PMA : UGX_ADV_PIN_PMH;
+    // bitap vs PM4 thresholds of the x86 SIMD builds (MAX_PATTERN_MIN{1,2,3}_NPY, lib/matcher.cpp:782-794)
+    switch (pf.min)
+    {
+      case 0:
+      case 1: return pf.npy <= 33 ? UGX_ADV_MIN1 : UGX_ADV_PMA;
+      case 2: return pf.npy <= 36 ? UGX_ADV_MIN2 : UGX_ADV_PMA;
+      case 3: return pf.npy <= 47 ? UGX_ADV_MIN3 : UGX_ADV_PMA;
+      default: return UGX_ADV_MIN4;
+    }
+  }
+  if (pf.len == 1)
+    return pf.min == 0 ? UGX_ADV_CHAR : pf.min < 4 ? UGX_ADV_CHAR_PMA : UGX_ADV_CHAR_PMH;
+  // advance_chars<2|3>, advance_string and advance_string_bm are exact literal searches that differ
+  // only in how they skip; one predicate covers them
+  return pf.min == 0 ? UGX_ADV_STRING : pf.min < 4 ? UGX_ADV_STRING_PMA : UGX_ADV_STRING_PMH;
+}
+
+namespace {
+
+struct RawState {
+  uint32_t accept = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> metas; // (code, target word)
+  uint32_t target[256];                             // target word or NONE
+};
+
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+
+int parse_state(const uint32_t* opc, uint32_t nop, uint32_t s, RawState& st, std::string& err)
+{
+  uint32_t i = s;
+  auto word = [&](uint32_t k) -> uint32_t { return k < nop ? opc[k] : OP_HALT; };
+  if (s >= nop)
+  {
+    err = "jump outside the opcode table";
+    return UGX_E_INVALID;
+  }
+  uint32_t op = word(i);
+  if (!op_is_goto(op) && (op >> 24) == 0xfe)
+  {
+    st.accept = op & 0xffffff;
+    op = word(++i);
+  }
+  while (!op_is_goto(op))
+  {
+    uint32_t code = op >> 24;
+    if (code == 0xfd || code == 0xfc || code == 0xfb)
+    {
+      err = "REDO/TAIL/HEAD opcodes (lookahead, negative patterns) are outside the path's scope";
+      return UGX_E_UNSUPPORTED;
+    }
+    if (code == 0xfe)
+    {
+      err = "unexpected TAKE inside a state";
+      return UGX_E_INVALID;
+    }
+    if (code == 0xff)
+    {
+      op = word(++i);
+      continue;
+    }
+    if (code == 0 || code > 0x0c)
+    {
+      err = "indent/dedent META opcodes are outside the path's scope";
+      return UGX_E_UNSUPPORTED;
+    }
+    uint32_t idx = op & 0xffff;
+    if (idx == IDX_LONG)
+      idx = word(++i) & 0xffffff;
+    else if (idx == IDX_HALT)
+    {
+      err = "META edge to the dead state";
+      return UGX_E_INVALID;
+    }
+    st.metas.emplace_back(code, idx);
+    op = word(++i);
+    if (i > nop)
+    {
+      err = "unterminated state";
+      return UGX_E_INVALID;
+    }
+  }
+  const uint32_t g0 = i;
+  for (uint32_t b = 0; b < 256; ++b)
+  {
+    uint32_t j = g0;
+    uint32_t o = word(j);
+    while (b < (o >> 24) || b > ((o >> 16) & 0xff))
+    {
+      o = word(++j);
+      if (j > nop)
+      {
+        err = "unterminated goto list";
+        return UGX_E_INVALID;
+      }
+    }
+    uint32_t idx = o & 0xffff;
+    if (idx == IDX_HALT)
+      st.target[b] = NONE;
+    else if (idx == IDX_LONG)
+      st.target[b] = word(j + 1) & 0xffffff;
+    else
+      st.target[b] = idx;
+  }
+  return UGX_OK;
+}
+
+} // namespace
+
+int flatten_dfa(const uint32_t* opc, uint32_t nop, HostDfa& out, std::string& err)
+{
+  if (opc == nullptr || nop == 0)
+  {
+    err = "empty opcode table";
+    return UGX_E_INVALID;
+  }
+  std::map<uint32_t, uint32_t> id_of; // word index -> dense id (BFS order, start = 0)
+  std::vector<RawState> states;
+  std::vector<uint32_t> word_of;
+  std::queue<uint32_t> todo;
+  id_of[0] = 0;
+  word_of.push_back(0);
+  todo.push(0);
+  while (!todo.empty())
+  {
+    uint32_t w = todo.front();
+    todo.pop();
+    RawState st;
+    int rc = parse_state(opc, nop, w, st, err);
+    if (rc != UGX_OK)
+      return rc;
+    auto visit = [&](uint32_t t) {
+      if (t != NONE && id_of.find(t) == id_of.end())
+      {
+        id_of[t] = static_cast<uint32_t>(word_of.size());
+        word_of.push_back(t);
+        todo.push(t);
+      }
+    };
+    for (uint32_t b = 0; b < 256; ++b)
+      visit(st.target[b]);
+    for (auto& m : st.metas)
+      visit(m.second);
+    if (states.size() <= id_of[w])
+      states.resize(id_of[w] + 1);
+    states[id_of[w]] = st;
+    if (word_of.size() >= DEAD)
+    {
+      err = "more than 65534 DFA states";
+      return UGX_E_UNSUPPORTED;
+    }
+  }
+  const uint32_t ns = static_cast<uint32_t>(word_of.size());
+  states.resize(ns);
+  // byte equivalence classes: bytes with identical columns
+  std::map<std::vector<uint32_t>, uint32_t> col_id;
+  uint32_t ncls = 0;
+  std::vector<uint32_t> rep; // representative byte per class
+  for (uint32_t b = 0; b < 256; ++b)
+  {
+    std::vector<uint32_t> col(ns);
+    for (uint32_t s = 0; s < ns; ++s)
+      col[s] = states[s].target[b];
+    auto it = col_id.find(col);
+    if (it == col_id.end())
+    {
+      col_id[col] = ncls;
+      out.cls[b] = static_cast<uint8_t>(ncls);
+      rep.push_back(b);
+      ++ncls;
+    }
+    else
+    {
+      out.cls[b] = static_cast<uint8_t>(it->second);
+    }
+  }
+  out.nstates = ns;
+  out.ncls = ncls;
+  out.next.assign(static_cast<size_t>(ns) * ncls, DEAD);
+  out.accept.assign(ns, 0);
+  out.word_of = word_of;
+  out.meta_off.assign(ns + 1, 0);
+  out.metas.clear();
+  out.has_meta = false;
+  out.newline_live = false;
+  out.to_start = false;
+  for (uint32_t s = 0; s < ns; ++s)
+  {
+    out.accept[s] = states[s].accept;
+    for (uint32_t c = 0; c < ncls; ++c)
+    {
+      uint32_t t = states[s].target[rep[c]];
+      if (t != NONE)
+      {
+        uint32_t id = id_of[t];
+        out.next[static_cast<size_t>(s) * ncls + c] = static_cast<uint16_t>(id);
+        if (id == 0)
+          out.to_start = true;
+      }
+    }
+    if (states[s].target['\n'] != NONE)
+      out.newline_live = true;
+    out.meta_off[s] = static_cast<uint32_t>(out.metas.size());
+    for (auto& m : states[s].metas)
+    {
+      out.metas.push_back(MetaEdge{m.first, id_of[m.second]});
+      out.has_meta = true;
+    }
+  }
+  out.meta_off[ns] = static_cast<uint32_t>(out.metas.size());
+  return UGX_OK;
+}
+
+int check_scope(const HostDfa& dfa, const ugx_prefilter& pf, uint32_t matcher_flags, std::string& err)
+{
+  if (matcher_flags & UGX_OPT_N)
+  {
+    err = "matcher option N (empty matches, ugrep -Y) is outside the path's scope";
+    return UGX_E_UNSUPPORTED;
+  }
+  if (dfa.newline_live)
+  {
+    err = "the DFA has a transition on '\\n': matches are not line-local";
+    return UGX_E_UNSUPPORTED;
+  }
+  if (pf.lbk != 0 && (pf.cbk['\n' >> 3] >> ('\n' & 7) & 1))
+  {
+    err = "look-back set contains '\\n'";
+    return UGX_E_UNSUPPORTED;
+  }
+  if (pf.len > 255 || pf.min > 8 || pf.pin > 16 || (pf.len == 0 && pf.pin > 0 && (pf.lcp >= 8 || pf.lcs >= 8)))
+  {
+    err = "prefilter fields out of range";
+    return UGX_E_INVALID;
+  }
+  if (pf.len > 0)
+    for (uint32_t i = 0; i < pf.len; ++i)
+      if (pf.chr[i] == '\n')
+      {
+        err = "literal prefix contains '\\n'";
+        return UGX_E_UNSUPPORTED;
+      }
+  return UGX_OK;
+}
+
+} // namespace ugx

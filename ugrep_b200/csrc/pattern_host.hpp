@@ -1,0 +1,51 @@
+// pattern_host.hpp — host-side "DFA export": reflex::Pattern opcode words -> dense,
+// byte-class-compressed transition table + the prefilter routine selection.
+// No CUDA here: this part is unit-tested on the CPU.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/ugrep_b200.h"
+
+namespace ugx {
+
+constexpr uint32_t OP_HALT = 0x00FFFFFFu;
+constexpr uint32_t IDX_HALT = 0xFFFFu;
+constexpr uint32_t IDX_LONG = 0xFFFEu;
+constexpr uint16_t DEAD = 0xFFFFu;
+
+// opcode codec, /root/reference/include/reflex/pattern.h:1155-1247
+inline bool op_is_goto(uint32_t op) { return (op << 8) >= (op & 0xff000000u); }
+
+struct MetaEdge {
+  uint32_t code;   // META code - 0x100 (pattern.h:930-952)
+  uint32_t target; // dense state id
+};
+
+struct HostDfa {
+  uint32_t nstates = 0;
+  uint32_t ncls = 0;
+  uint8_t cls[256] = {0};          // byte -> equivalence class
+  std::vector<uint16_t> next;      // [nstates * ncls], DEAD = no transition
+  std::vector<uint32_t> accept;    // [nstates] accept index (TAKE), 0 = none
+  std::vector<uint32_t> word_of;   // [nstates] opcode word index of the state
+  std::vector<uint32_t> meta_off;  // [nstates + 1] offsets into metas
+  std::vector<MetaEdge> metas;
+  bool has_meta = false;
+  bool newline_live = false;       // some state has a transition on '\n'
+  bool to_start = false;           // some transition targets state 0 (start-loop skip, lib/matcher.cpp:504-527)
+  uint32_t table_bytes() const { return nstates * ncls * 2; }
+};
+
+// Matcher::init_advance, /root/reference/lib/matcher.cpp:797-954
+int select_advance(const ugx_prefilter& pf, uint32_t matcher_flags);
+
+// returns UGX_OK or an error status; err receives a message
+int flatten_dfa(const uint32_t* opc, uint32_t nop, HostDfa& out, std::string& err);
+
+// checks that make the line-parallel scan exact for this pattern (DESIGN.md "line locality")
+int check_scope(const HostDfa& dfa, const ugx_prefilter& pf, uint32_t matcher_flags, std::string& err);
+
+} // namespace ugx
