@@ -1,0 +1,383 @@
+#!/usr/bin/env python3
+"""bench.py — GB/s scanned by the B200 buffer-scan path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2]
+
+One "step" = one pass of the hot path over one batch: `ugrep -c -F -f words.txt`
+(config c2, the 1,000-literal alternation) over a 4 GiB synthetic corpus per GPU.
+N > 1 is launched by torch.distributed.run, one rank per GPU; the corpus shards
+by line-aligned piece (one per rank, no data-path collective); NCCL only
+all-gathers the per-shard counts and newline counts (line-number bases).
+
+value  = whole-job GB/s with the corpus resident in HBM (CUDA events, max over ranks)
+e2e    = the same through the C ABI with HOST (pinned) buffers: H2D inside the timed region
+roofline / cpu_baseline: see DESIGN.md "measurement".
+
+--impl reference times the reference's own CPU implementation (oracle/_ref/ugrep, the
+unmodified reference built from /root/reference) with all host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GIB = 1 << 30
+
+# config -> (pattern file, corpus generator name, scan mode, reference CLI args, default GiB per GPU)
+CONFIGS = {
+    "c1": ("c1", "c1", "lines", ["-c", "-F", "Sherlock Holmes"], 1),
+    "c2": ("c2", "c2", "lines", ["-c", "-F", "-f", "@WORDS@"], 4),
+    "c3b": ("c3b", "c3", "list", ["-n", "-b", "-o", "[A-Z][a-z]+ing"], 4),
+    "c4": ("c4", "c4", "lines", ["-i", "-c", "\\p{Greek}+|naïve\\w*"], 8),
+    "c5": ("c5", "c5", "matches", ["-c", "-o", "-e", "ERROR|WARN", "-e", "\\d{3}-\\d{4}"], 8),
+}
+WORKLOAD_TEXT = {
+    "c1": "ugrep -c -F 'Sherlock Holmes' over synthetic ASCII text",
+    "c2": "ugrep -c -F -f words.txt (1,000-literal alternation) over synthetic text",
+    "c3b": "ugrep -n -b -o '[A-Z][a-z]+ing' (match records) over synthetic text",
+    "c4": "ugrep -i -c '\\p{Greek}+|naïve\\w*' over mixed UTF-8",
+    "c5": "ugrep -c -o -e 'ERROR|WARN' -e '\\d{3}-\\d{4}' over a synthetic log corpus",
+}
+PAT_DIR = os.path.join(ROOT, "ugrep_b200", "patterns")
+REF_UGREP = os.path.join(ROOT, "oracle", "_ref", "ugrep")
+BLOCK_BYTES = 64 << 20
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.samples = []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.samples.append([x.strip() for x in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i] == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_block(cfg: str):
+    from ugrep_b200 import corpus
+    return corpus.block(CONFIGS[cfg][1], BLOCK_BYTES)
+
+
+# ---------------------------------------------------------------- reference arm (CPU)
+
+def reference_run(cfg: str, sample_bytes: int, steps: int, warmup: int):
+    """Time `ugrep -J<cores>` over the sample split into line-aligned files (ugrep parallelises per file)."""
+    import numpy as np
+    if not os.access(REF_UGREP, os.X_OK):
+        return None
+    cores = os.cpu_count() or 1
+    block = make_block(cfg)
+    reps = max(1, sample_bytes // block.size)
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    d = tempfile.mkdtemp(prefix="ugx_ref_", dir=shm)
+    try:
+        nfiles = min(cores, 64)
+        # cut the tiled sample into nfiles line-aligned pieces: each piece = some whole blocks + a line-aligned slice
+        total = block.size * reps
+        nl = np.flatnonzero(block == 10)
+        files = []
+        pos = 0
+        for i in range(nfiles):
+            target = total * (i + 1) // nfiles
+            b, off = divmod(target, block.size)
+            if i == nfiles - 1:
+                endpos = total
+            else:
+                j = np.searchsorted(nl, off)
+                endpos = b * block.size + (int(nl[j]) + 1 if j < len(nl) else block.size)
+            path = os.path.join(d, "shard_%03d.txt" % i)
+            with open(path, "wb") as f:
+                p = pos
+                while p < endpos:
+                    o = p % block.size
+                    take = min(block.size - o, endpos - p)
+                    f.write(block[o:o + take].tobytes())
+                    p += take
+            files.append(path)
+            pos = endpos
+        args = [a if a != "@WORDS@" else os.path.join(PAT_DIR, "words.txt") for a in CONFIGS[cfg][3]]
+        cmd = [REF_UGREP, "--no-config", "-J%d" % cores, *args, *files]
+        times = []
+        out = b""
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, capture_output=True)
+            dt = time.perf_counter() - t0
+            if r.returncode not in (0, 1):
+                raise RuntimeError("reference ugrep failed: %s" % r.stderr[:200])
+            if it >= warmup:
+                times.append(dt)
+            out = r.stdout
+        count = 0
+        for line in out.splitlines():
+            tail = line.rsplit(b":", 1)[-1]
+            if tail.isdigit():
+                count += int(tail)
+        sec = sum(times) / len(times)
+        return {"gbs": total / sec / 1e9, "seconds": sec, "cores": cores, "files": nfiles, "bytes": total,
+                "count": count, "best_gbs": total / min(times) / 1e9}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+# ---------------------------------------------------------------- our arm (GPU)
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--gib", type=float, default=None, help="GiB per GPU (default: the config's named size)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--others", action="store_true", help="also time the other configs briefly (extra keys)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = args.config
+    gib = args.gib if args.gib is not None else CONFIGS[cfg][4]
+    peak, peak_kind = peaks()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = int(min(gib * GIB, 2 * GIB))
+        r = reference_run(cfg, sample, max(1, args.steps), max(1, min(args.warmup, 1)))
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ugrep is not built"}))
+            return 0
+        line = {
+            "impl": "reference", "metric": "GB/s scanned", "value": round(r["gbs"], 3), "unit": "GB/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(r["seconds"] * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "%s, %.2f GiB sample in %d line-aligned files" % (WORKLOAD_TEXT[cfg], r["bytes"] / GIB, r["files"]),
+                       "config": cfg},
+            "cpu_baseline": {"value": round(r["gbs"], 3), "unit": "GB/s", "cores": r["cores"], "kind": "reference",
+                             "sample": "%.2f GiB of the %s corpus, ugrep -J%d over %d files, page cache warm"
+                                       % (r["bytes"] / GIB, cfg, r["cores"], r["files"])},
+            "e2e": {"value": round(r["gbs"], 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "count": r["count"],
+        }
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ugrep_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the scan path is CUDA-only; there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- corpus: one seeded block, tiled on the device to the named size (line-aligned, so still valid text)
+    block = make_block(cfg)
+    reps = max(1, int(gib * GIB) // block.size)
+    nbytes = block.size * reps
+    dblock = torch.from_numpy(block).cuda()
+    corpus_dev = dblock.repeat(reps)
+    del dblock
+    pat = api.Pattern.load(os.path.join(PAT_DIR, CONFIGS[cfg][0] + ".ugxp"), local)
+    stream = torch.cuda.current_stream().cuda_stream
+    sc = api.Scanner(local, stream)
+    mode = CONFIGS[cfg][2]
+
+    def step(data):
+        if mode == "lines":
+            return sc.count_lines(pat, data)
+        if mode == "matches":
+            return sc.count_matches(pat, data)
+        return sc.find_all_device(pat, data)
+
+    # expected result from one block (size-independent check: counts scale with the number of tiles)
+    t1 = step(torch.from_numpy(block).cuda())
+    expect = t1.matches * reps
+
+    for _ in range(args.warmup):
+        tot = step(corpus_dev)
+    if tot.matches != expect:
+        raise SystemExit("bench.py: wrong count %d != %d x %d" % (tot.matches, t1.matches, reps))
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    kernel_ms = []
+    launches = 0
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        tot = step(corpus_dev)
+        kernel_ms.append(tot.kernel_ms)
+        launches += tot.launches
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tm = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+        # the one exchange step of the path: per-shard {matches, newlines} -> totals and line-number bases
+        mine = torch.tensor([tot.matches, tot.newlines], dtype=torch.int64, device="cuda")
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        total_matches = int(sum(int(v[0]) for v in allv))
+    else:
+        total_matches = tot.matches
+    ms_per_step = ms / args.steps
+    value = world * nbytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: host (pinned) buffer through the C ABI, H2D + scan + D2H of the result inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        hb = host.numpy()
+        for i in range(reps):
+            hb[i * block.size:(i + 1) * block.size] = block
+        for _ in range(2):
+            th = step(hb)
+        if th.matches != expect:
+            raise SystemExit("bench.py: wrong e2e count")
+        esteps = max(3, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            th = step(hb)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tm = torch.tensor([dt], device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dt = float(tm.item())
+        e2e = {"value": round(world * nbytes * esteps / dt / 1e9, 3), "unit": "GB/s",
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 32, "steps": esteps}
+        del host, hb
+
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+
+    others = {}
+    if args.others and rank == 0:
+        for oc in CONFIGS:
+            if oc == cfg:
+                continue
+            ob = make_block(oc)
+            orep = max(1, (1 * GIB) // ob.size)
+            od = torch.from_numpy(ob).cuda().repeat(orep)
+            op = api.Pattern.load(os.path.join(PAT_DIR, CONFIGS[oc][0] + ".ugxp"), local)
+            om = CONFIGS[oc][2]
+            best = None
+            for _ in range(4):
+                if om == "lines":
+                    t = sc.count_lines(op, od)
+                elif om == "matches":
+                    t = sc.count_matches(op, od)
+                else:
+                    t = sc.find_all_device(op, od)
+                best = t.kernel_ms if best is None else min(best, t.kernel_ms)
+            gbs = od.numel() / (best * 1e-3) / 1e9
+            others[oc] = {"gbs": round(gbs, 2), "hbm_frac": round(gbs / peak, 4), "gib": round(od.numel() / GIB, 2),
+                          "result": t.matches}
+            del od
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            r = reference_run(cfg, min(nbytes, 1 * GIB), 2, 1)
+            if r is not None:
+                cpu = {"value": round(r["gbs"], 3), "unit": "GB/s", "cores": r["cores"], "kind": "reference",
+                       "sample": "%.2f GiB of the %s corpus in %d line-aligned files, oracle/_ref/ugrep -J%d, page cache warm, mean of 2"
+                                 % (r["bytes"] / GIB, cfg, r["files"], r["cores"])}
+        except Exception as ex:  # the baseline is reported, never required
+            cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % ex}
+
+    if rank == 0:
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        achieved = nbytes / (k_ms * 1e-3) / 1e9
+        info = pat.info
+        line = {
+            "metric": "GB/s scanned", "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "%s, %.2f GiB per GPU (%d x %d MiB seeded block, line-aligned)"
+                                   % (WORKLOAD_TEXT[cfg], nbytes / GIB, reps, block.size >> 20),
+                       "config": cfg, "l2": "input (%.1f GiB) larger than L2" % (nbytes / GIB),
+                       "sharding": "one line-aligned shard per GPU, NCCL all-gather of counts only",
+                       "dfa_states": info["states"], "byte_classes": info["classes"], "prefilter": info["advance_name"],
+                       "table_in_smem": bool(info["table_in_smem"])},
+            "hbm_frac": round(value / world / peak, 4),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "peak_kind": peak_kind,
+                         "kernel": "scan_lines_kernel", "kernel_ms": round(k_ms, 4)},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "result": {"count": total_matches, "expected_per_gpu": expect},
+        }
+        if others:
+            line["others"] = others
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

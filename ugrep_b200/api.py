@@ -163,6 +163,23 @@ class Scanner:
         _check(lib().ugx_count_matches(self._h, pattern._h, C.c_void_p(ptr), n, C.byref(t)))
         return self._totals(t)
 
+    def find_all_device(self, pattern: Pattern, data, base_offset: int = 0, base_line: int = 0) -> Totals:
+        """Like find_all but the records stay on the device (fetch() copies a range to the host)."""
+        ptr, n, keep = _buffer(data)
+        t = _Totals()
+        dev = C.c_void_p()
+        cnt = C.c_uint64()
+        _check(lib().ugx_find_all_device(self._h, pattern._h, C.c_void_p(ptr), n, base_offset, base_line,
+                                         C.byref(dev), C.byref(cnt), C.byref(t)))
+        self.last_records = (dev.value, cnt.value)
+        return self._totals(t)
+
+    def fetch(self, first: int, count: int) -> np.ndarray:
+        out = np.zeros(count, dtype=MATCH_DTYPE)
+        if count:
+            _check(lib().ugx_scanner_fetch(self._h, out.ctypes.data, first, count))
+        return out
+
     def find_all(self, pattern: Pattern, data, base_offset: int = 0, base_line: int = 0):
         """All matches in input order as a structured array (line, offset, len, cap) + totals."""
         ptr, n, keep = _buffer(data)
