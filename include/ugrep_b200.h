@@ -146,6 +146,8 @@ void ugx_pattern_destroy(ugx_pattern *p);
 /* scanner: owns a stream-ordered scratch arena on `device`; `stream` is a cudaStream_t (NULL = default stream) */
 int  ugx_scanner_create(int device, void *stream, ugx_scanner **out);
 void ugx_scanner_destroy(ugx_scanner *s);
+/* options: "force_generic" = 1 makes every scan take the generic line-scan kernel (used by the tests) */
+int  ugx_scanner_set_option(ugx_scanner *s, const char *name, int value);
 
 /*
  * Scans.  `buf` is nbytes of text; it may be a device pointer (scanned in place)

@@ -27,7 +27,7 @@ ADVANCE_NAMES = ["none", "pin1_one", "pin1_pma", "pin1_pmh", "pin_one", "pin_pma
 
 EXPORTS = ["ugx_last_error", "ugx_abi_version", "ugx_pattern_create", "ugx_pattern_load", "ugx_pattern_info_get",
            "ugx_pattern_destroy", "ugx_scanner_create", "ugx_scanner_destroy", "ugx_count_lines", "ugx_count_matches",
-           "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_count_newlines"]
+           "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_scanner_set_option", "ugx_count_newlines"]
 
 
 class UgxError(RuntimeError):
@@ -82,6 +82,7 @@ def lib():
                                    C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(_Totals)]
         L.ugx_find_all_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64,
                                           C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(_Totals)]
+        L.ugx_scanner_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.ugx_scanner_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
         _lib = L
     return _lib
@@ -147,6 +148,9 @@ class Scanner:
         self._h = C.c_void_p()
         self.device = device
         _check(lib().ugx_scanner_create(device, C.c_void_p(stream or 0), C.byref(self._h)))
+
+    def set_option(self, name: str, value: int) -> None:
+        _check(lib().ugx_scanner_set_option(self._h, name.encode(), int(value)))
 
     def _totals(self, t: _Totals) -> Totals:
         return Totals(t.matches, t.newlines, t.long_lines, t.kernel_ms, t.launches)

@@ -105,6 +105,7 @@ struct ugx_scanner {
   uint64_t records_cap = 0;
   uint64_t records_n = 0;
   uint8_t* stage = nullptr; // device copy of a host buffer
+  bool force_generic = false; // tests: always take the generic line-scan kernel
   uint64_t stage_cap = 0;
 };
 
@@ -346,7 +347,17 @@ int resolve(ugx_scanner* s, const void* buf, uint64_t n, const uint8_t** dev, ui
   cudaError_t e = cudaPointerGetAttributes(&at, buf);
   if (e == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged))
   {
-    *dev = static_cast<const uint8_t*>(buf);
+    if ((reinterpret_cast<uintptr_t>(buf) & 15) == 0)
+    {
+      *dev = static_cast<const uint8_t*>(buf);
+      return UGX_OK;
+    }
+    // the kernels use 16-byte vector loads: a misaligned device buffer is copied to aligned scratch
+    int rc = ensure(s->stage, s->stage_cap, n + 16);
+    if (rc != UGX_OK)
+      return rc;
+    CU(cudaMemcpyAsync(s->stage, buf, n, cudaMemcpyDeviceToDevice, s->stream));
+    *dev = s->stage;
     return UGX_OK;
   }
   if (e != cudaSuccess)
@@ -408,9 +419,17 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
   a.base_offset = base_offset;
   a.base_line = base_line;
   CU(cudaEventRecord(s->ev0, s->stream));
-  CU(ugx::launch_scan_lines(p->dev, a, mode, false, s->sm_count, s->stream));
-  CU(ugx::launch_tile_prefix(s->tile_matches, s->tile_newlines, ntiles, s->totals, s->stream));
-  tt.launches = 2;
+  if (mode == 0 && !want_records && !s->force_generic && ugx::count_lines_any_eligible(p->dev))
+  {
+    CU(ugx::launch_count_lines_any(p->dev, dbuf, n, s->totals, s->sm_count, s->stream));
+    tt.launches = 1;
+  }
+  else
+  {
+    CU(ugx::launch_scan_lines(p->dev, a, mode, false, s->sm_count, s->stream));
+    CU(ugx::launch_tile_prefix(s->tile_matches, s->tile_newlines, ntiles, s->totals, s->stream));
+    tt.launches = 2;
+  }
   CU(cudaMemcpyAsync(s->h_totals, s->totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
   if (want_records)
   {
@@ -484,6 +503,18 @@ int ugx_find_all(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t
     CU(cudaStreamSynchronize(s->stream));
   }
   return UGX_OK;
+}
+
+int ugx_scanner_set_option(ugx_scanner* s, const char* name, int value)
+{
+  if (s == nullptr || name == nullptr)
+    return fail(UGX_E_INVALID, "null argument");
+  if (strcmp(name, "force_generic") == 0)
+  {
+    s->force_generic = value != 0;
+    return UGX_OK;
+  }
+  return fail(UGX_E_INVALID, std::string("unknown scanner option ") + name);
 }
 
 int ugx_scanner_fetch(ugx_scanner* s, ugx_match* out, uint64_t first, uint64_t count)

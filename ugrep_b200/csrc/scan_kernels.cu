@@ -12,345 +12,13 @@
 // Records (ugrep -o) come from a second run of scan_lines_kernel that knows every strip's
 // output offset: deterministic input order, no atomics in the ordering.
 #include "device_pattern.cuh"
+#include "line_match.cuh"
 #include "scan_kernels.hpp"
+#include "tile_phase_a.cuh"
 
 namespace ugx {
 
 namespace {
-
-constexpr int LINE_DONE = 2;
-
-__device__ __forceinline__ bool advance_to(const Text& t, const DevPattern& P, const Tables& T, Cursor& m,
-                                           uint64_t loc, uint64_t last)
-{
-  // first candidate in [loc, last]; `last` is the line's '\n' (or the final byte of the buffer)
-  for (uint64_t k = loc; k <= last && k < t.end; ++k)
-  {
-    if (cand(t, P, T, k))
-    {
-      set_current(t, m, k);
-      return true;
-    }
-  }
-  return false;
-}
-
-// one anchored attempt over the dense table (patterns without META edges); lib/matcher.cpp:125-150, 446-546
-__device__ __forceinline__ int run_dfa_table(const Text& t, const DevPattern& P, const Tables& T, Cursor& m, uint32_t& retry)
-{
-  const bool W = (P.flags & UGX_OPT_W) != 0;
-  m.cap = 0;
-  if (W && !at_wb(t, P, m))
-    return 0;
-  uint32_t state = 0;
-  for (;;)
-  {
-    uint32_t acc = __ldg(P.accept + state);
-    if ((acc & 0x7fffffffu) != 0 && (!W || at_we(t, P, peek_ch(t, m), m.pos)))
-    {
-      m.cap = acc & 0x7fffffffu;
-      m.cur = m.pos;
-    }
-    if (acc & 0x80000000u) // state without outgoing edges: HALT before reading
-      break;
-    if (m.pos >= t.end)
-      break;
-    uint32_t ch = t.raw(m.pos++);
-    uint32_t nxt = T.next[state * P.ncls + T.cls[ch]];
-    if (nxt == D_DEAD)
-      break;
-    if (nxt == 0 && m.cap == 0) // back at the start state without an accept, lib/matcher.cpp:504-527
-    {
-      if (m.cur + 1 == m.pos)
-      {
-        ++m.cur;
-        if (retry > 0)
-          --retry;
-      }
-      else
-      {
-        while (m.cur + 1 < m.pos && !bit256(P.fst, t.raw(m.cur + 1)))
-        {
-          ++m.cur;
-          if (retry > 0)
-            --retry;
-        }
-      }
-    }
-    state = nxt;
-  }
-  return 0;
-}
-
-// one anchored attempt with the opcode interpreter (patterns with META edges); lib/matcher.cpp:94-546
-__device__ int run_dfa_opc(const Text& t, const DevPattern& P, Cursor& m, uint32_t& retry)
-{
-  const bool W = (P.flags & UGX_OPT_W) != 0;
-  const uint32_t* __restrict__ opc = P.opc;
-  int ch = m.got;
-  const bool bol = m.got == '\n';
-  m.cap = 0;
-  if (W && !at_wb(t, P, m))
-    return 0;
-  if (P.bol && !bol) // ^-anchored pattern away from a line start: the rest of this line cannot match
-    return LINE_DONE;
-  uint32_t pc = 0;
-  uint32_t back = D_NONE;
-  uint64_t bpos = 0;
-  for (;;)
-  {
-    uint32_t op = __ldg(opc + pc);
-    uint32_t jump;
-    if (!d_op_is_goto(op))
-    {
-      if ((op >> 24) == 0xfe)
-      {
-        if (!W || at_we(t, P, peek_ch(t, m), m.pos))
-        {
-          m.cap = op & 0xffffff;
-          m.cur = m.pos;
-        }
-        ++pc;
-        continue;
-      }
-      if (ch == D_EOF)
-        break;
-      ch = get_ch(t, m);
-      int metas = 5;
-      jump = D_NONE;
-      for (;;)
-      {
-        if (jump == D_NONE || back == D_NONE)
-        {
-          if (!d_op_is_goto(op))
-          {
-            uint32_t code = op >> 24;
-            if (code == 0xfe)
-            {
-              if (!W || at_we(t, P, ch, m.pos - 1))
-              {
-                m.cap = op & 0xffffff;
-                m.cur = m.pos;
-                if (ch != D_EOF)
-                  --m.cur;
-              }
-            }
-            else if (code != 0xff)
-            {
-              if (metas > 0 && jump == D_NONE && meta_holds(t, P, m, code, ch, bol))
-              {
-                --metas;
-                jump = op & 0xffff;
-                if (jump == D_IDX_LONG)
-                  jump = __ldg(opc + ++pc) & 0xffffff;
-              }
-            }
-            op = __ldg(opc + ++pc);
-            continue;
-          }
-          else if (ch != D_EOF && op != D_OP_HALT)
-          {
-            if (jump == D_NONE)
-              break;
-            if (back == D_NONE)
-            {
-              back = pc;
-              bpos = m.pos - m.txt - 1;
-            }
-          }
-        }
-        if (jump == D_NONE)
-        {
-          if (back != D_NONE && bpos + 1 == m.pos - m.txt)
-          {
-            pc = back;
-            op = __ldg(opc + pc);
-            back = D_NONE;
-          }
-          break;
-        }
-        if (back == pc)
-          bpos = m.pos - m.txt - 1;
-        pc = jump;
-        op = __ldg(opc + pc);
-        jump = D_NONE;
-      }
-      if (ch == D_EOF)
-        break;
-    }
-    else
-    {
-      if (op == D_OP_HALT)
-      {
-        if (back != D_NONE)
-        {
-          m.pos = m.txt + bpos;
-          pc = back;
-          back = D_NONE;
-          continue;
-        }
-        break;
-      }
-      if (ch == D_EOF)
-        break;
-      ch = get_ch(t, m);
-      if (ch == D_EOF)
-        break;
-    }
-    while (static_cast<uint32_t>(ch) < (op >> 24) || static_cast<uint32_t>(ch) > ((op >> 16) & 0xff))
-      op = __ldg(opc + ++pc);
-    jump = op & 0xffff;
-    if (jump == 0)
-    {
-      if (m.cap == 0)
-      {
-        if (m.cur + 1 == m.pos)
-        {
-          ++m.cur;
-          if (retry > 0)
-            --retry;
-        }
-        else
-        {
-          while (m.cur + 1 < m.pos && !bit256(P.fst, t.raw(m.cur + 1)))
-          {
-            ++m.cur;
-            if (retry > 0)
-              --retry;
-          }
-        }
-      }
-    }
-    else if (jump >= D_IDX_LONG)
-    {
-      if (jump == D_IDX_HALT)
-      {
-        if (back != D_NONE)
-        {
-          pc = back;
-          m.pos = m.txt + bpos;
-          back = D_NONE;
-          continue;
-        }
-        break;
-      }
-      jump = __ldg(opc + pc + 1) & 0xffffff;
-    }
-    pc = jump;
-  }
-  return 0;
-}
-
-__device__ __forceinline__ uint32_t look_back(const Text& t, const DevPattern& P, Cursor& m, uint64_t floor_pos)
-{
-  // walk back over cbk_ bytes from cur-1 down to floor_pos; lib/matcher.cpp:54-70, 639-654
-  uint32_t retry = 0;
-  uint64_t s = m.cur;
-  if (s > floor_pos)
-  {
-    uint64_t n = s - floor_pos;
-    if (P.lbk != 0xffff && P.lbk < n)
-      n = P.lbk;
-    while (n-- > 0 && bit256(P.cbk, t.raw(s - 1)))
-    {
-      --s;
-      ++retry;
-    }
-    m.cur -= retry;
-    retry = retry > P.lbm ? retry - P.lbm : 0;
-  }
-  return retry;
-}
-
-// one Matcher::match(FIND) confined to the line whose '\n' (or last byte) is at `last`.
-// returns the accept index, or 0 when the line has no further match
-template <bool HAS_META>
-__device__ uint32_t find_in_line(const Text& t, const DevPattern& P, const Tables& T, Cursor& m, uint64_t last)
-{
-  const bool W = (P.flags & UGX_OPT_W) != 0;
-  uint32_t retry = 0;
-  m.len = 0;
-  m.txt = m.cur;
-  if (!advance_to(t, P, T, m, m.cur, last))
-    return 0;
-  if (P.lbk > 0)
-  {
-    retry = look_back(t, P, m, m.txt);
-  }
-  else if (P.one)
-  {
-    uint64_t k = m.cur + P.len;
-    int ch = k < t.end ? static_cast<int>(t.raw(k)) : D_EOF;
-    if (!W || (at_wb(t, P, m) && (m.pos >= t.end || at_we(t, P, ch, k))))
-    {
-      m.txt = m.cur;
-      m.len = P.len;
-      set_current(t, m, k);
-      return m.cap = 1;
-    }
-  }
-  set_current(t, m, m.cur);
-  for (;;)
-  {
-    m.txt = m.cur;
-    int r = HAS_META ? run_dfa_opc(t, P, m, retry) : run_dfa_table(t, P, T, m, retry);
-    if (r == LINE_DONE)
-      return 0;
-    if (m.cap == 0)
-    {
-      if (m.pos < t.end)
-      {
-        if (retry > 0)
-        {
-          --retry;
-          set_current(t, m, m.cur + 1);
-          continue;
-        }
-        if (m.cur < m.pos)
-        {
-          if (!advance_to(t, P, T, m, m.cur + 1, last))
-            return 0;
-          if (P.lbk > 0)
-          {
-            retry = look_back(t, P, m, m.txt + 1);
-            set_current(t, m, m.cur);
-            continue;
-          }
-          if (!P.one)
-            continue;
-          uint64_t k = m.cur + P.len;
-          int ch = k < t.end ? static_cast<int>(t.raw(k)) : D_EOF;
-          if (W && (!at_wb(t, P, m) || !(m.pos >= t.end || at_we(t, P, ch, k))))
-            continue;
-          m.txt = m.cur;
-          m.len = P.len;
-          set_current(t, m, k);
-          return m.cap = 1;
-        }
-      }
-      m.txt = m.cur;
-    }
-    m.len = static_cast<uint32_t>(m.cur - m.txt);
-    if (m.len == 0)
-    {
-      m.pos = m.cur;
-      if (m.pos >= t.end)
-        return 0;
-      if (m.cap != 0)
-      {
-        if (!advance_to(t, P, T, m, m.cur + 1, last))
-          return 0;
-        continue;
-      }
-      if (m.cur + 1 > last)
-        return 0;
-      set_current(t, m, m.cur + 1);
-      continue;
-    }
-    set_current(t, m, m.cur);
-    return m.cap;
-  }
-}
 
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane)
 {
@@ -393,7 +61,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_s
 
 // MODE 0: count matching lines (ugrep -c), 1: count matches (ugrep -c -o) / emit records (ugrep -o)
 template <int MODE, bool EMIT, bool HAS_META>
-__global__ void __launch_bounds__(SCAN_THREADS)
+__global__ void __launch_bounds__(SCAN_THREADS, 2)
 scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, uint64_t ntiles,
                   uint32_t stage_table, uint64_t* __restrict__ tile_matches, uint64_t* __restrict__ tile_newlines,
                   uint32_t* __restrict__ strip_counts, ugx_match* __restrict__ out, uint64_t out_cap,
@@ -405,7 +73,9 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
   uint8_t* s_cls = smem;
   uint8_t* s_pred = smem + 256;
   uint8_t* s_tap = s_pred + UGX_HASH;
-  uint16_t* s_next = reinterpret_cast<uint16_t*>(s_tap + UGX_BTAP);
+  uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_tap + UGX_BTAP);
+  uint32_t* s_nl = s_cand + SCAN_TILE / 32;
+  uint16_t* s_next = reinterpret_cast<uint16_t*>(s_nl + SCAN_TILE / 32);
   for (uint32_t i = threadIdx.x; i < 256 / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(s_cls)[i] = __ldg(reinterpret_cast<const uint32_t*>(P.cls) + i);
   for (uint32_t i = threadIdx.x; i < UGX_HASH / 16; i += blockDim.x)
@@ -425,36 +95,15 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
 
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
   {
-    const uint64_t s0 = tile * SCAN_TILE + static_cast<uint64_t>(threadIdx.x) * SCAN_STRIP;
+    const uint64_t tile_base = tile * SCAN_TILE;
+    const uint64_t s0 = tile_base + static_cast<uint64_t>(threadIdx.x) * SCAN_STRIP;
+    // ---- phase A: candidate and newline bitmaps of the tile (position-parallel prefilter)
+    tile_phase_a<SCAN_TILE / 16 / SCAN_THREADS>(t, P, T, tile_base, reinterpret_cast<uint16_t*>(s_cand),
+                                                reinterpret_cast<uint16_t*>(s_nl));
+    __syncthreads();
+    const CandMap cm{s_cand, tile_base, SCAN_TILE};
     // ---- newline mask of my strip and the line starts in it ----
-    uint64_t nl = 0;
-    if (s0 < n)
-    {
-      if (s0 + SCAN_STRIP <= n)
-      {
-        const uint4* q = reinterpret_cast<const uint4*>(buf + s0);
-#pragma unroll
-        for (int j = 0; j < SCAN_STRIP / 16; ++j)
-        {
-          uint4 v = __ldg(q + j);
-          uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-          {
-            uint32_t e = __vcmpeq4(w[k], 0x0a0a0a0au); // 0xff per equal byte
-            // gather the top bit of each byte into 4 bits
-            uint32_t bits = ((e & 0x80u) >> 7) | ((e & 0x8000u) >> 14) | ((e & 0x800000u) >> 21) | ((e & 0x80000000u) >> 28);
-            nl |= static_cast<uint64_t>(bits) << (j * 16 + k * 4);
-          }
-        }
-      }
-      else
-      {
-        for (uint32_t i = 0; s0 + i < n; ++i)
-          if (__ldg(buf + s0 + i) == '\n')
-            nl |= 1ull << i;
-      }
-    }
+    const uint64_t nl = (static_cast<uint64_t>(s_nl[2 * threadIdx.x + 1]) << 32) | s_nl[2 * threadIdx.x];
     uint64_t starts = nl << 1;
     if (s0 < n && (s0 == 0 || __ldg(buf + s0 - 1) == '\n'))
       starts |= 1ull;
@@ -503,7 +152,7 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
       set_current(t, m, L);
       for (;;)
       {
-        uint32_t cap = find_in_line<HAS_META>(t, P, T, m, last);
+        uint32_t cap = find_in_line<HAS_META>(t, P, T, cm, m, last);
         if (cap == 0)
           break;
         if (EMIT)
@@ -555,8 +204,8 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
         tile_matches[tile] = a;
         tile_newlines[tile] = b;
       }
-      __syncthreads();
     }
+    __syncthreads(); // the bitmaps are rewritten by the next tile
   }
 }
 
@@ -609,7 +258,7 @@ tile_prefix_kernel(uint64_t* __restrict__ tile_matches, uint64_t* __restrict__ t
 
 static size_t scan_smem_bytes(const DevPattern& P, bool stage)
 {
-  return 256 + UGX_HASH + UGX_BTAP + (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
+  return 256 + UGX_HASH + UGX_BTAP + 2 * (SCAN_TILE / 8) + (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
 }
 
 template <int MODE, bool EMIT, bool HAS_META>
