@@ -8,7 +8,7 @@
  * bench.py's cpu_baseline leg may load this; the product never does.
  *
  * Parity pin: tests/test_oracle_vs_reference.py checks this restatement against
- * the reference's own golden files (tests/out/*.out) and against the unmodified
+ * the reference's own golden files (tests/out/ *.out) and against the unmodified
  * reference built into oracle/_ref (ugrep CLI and libreflex in-place scans).
  */
 #ifndef UGX_ORACLE_H

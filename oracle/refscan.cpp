@@ -160,6 +160,12 @@ static int parse_popts(int argc, char **argv, int i, POpts& o, std::vector<std::
     else if (a == "-f" && i + 1 < argc) o.file = argv[++i];
     else rest.push_back(a);
   }
+  // CNF::anchor (src/cnf.hpp:167-204): without -w/-x, a pattern that starts with ^ or ends with $ switches -Y on
+  // (after -F quoting the pattern starts with \Q, so -F never triggers it; -f FILE lines are not checked)
+  if (!o.F && !o.w)
+    for (size_t n = 0; n < o.pats.size(); ++n)
+      if (!o.pats[n].empty() && (o.pats[n][0] == '^' || o.pats[n][o.pats[n].size() - 1] == '$'))
+        o.Y = true;
   return i;
 }
 

@@ -97,7 +97,7 @@ class OraclePattern:
     def find_all(self, data, base_offset: int = 0, base_line: int = 0) -> np.ndarray:
         a = _as_u8(data)
         n = C.c_uint64()
-        cap = max(1024, a.size // 2 + 16)
+        cap = max(1024, a.size + 16)
         out = np.zeros(cap, dtype=MATCH_DTYPE)
         rc = lib().ora_find_all(self.handle, a.ctypes.data, a.size, base_offset, base_line,
                                 out.ctypes.data, cap, C.byref(n))
