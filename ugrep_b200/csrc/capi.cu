@@ -161,6 +161,10 @@ int ugx_pattern_create(const uint32_t* opc, uint32_t nop, const ugx_prefilter* p
   d.to_start = p->dfa.to_start;
   d.nop = nop;
   d.table_bytes = p->dfa.table_bytes();
+  d.first_acc = p->dfa.first_acc;
+  d.first_leaf = p->dfa.first_leaf;
+  d.acc0 = p->dfa.accept[0] != 0;
+  ugx::plan_filter(*pf, p->adv, d.plan);
   d.n_word_ranges = sizeof(k_word_ranges) / sizeof(int) / 2;
   memcpy(d.chr, pf->chr, 256);
   set256(d.cbk, pf->cbk);

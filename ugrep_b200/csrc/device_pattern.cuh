@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/ugrep_b200.h"
+#include "filter_plan.hpp"
 
 namespace ugx {
 
@@ -26,6 +27,7 @@ constexpr int D_EOF = -1;
 struct DevPattern {
   uint32_t adv, len, min, pin, lcp, lcs, one, bol, lbk, lbm, flags;
   uint32_t nstates, ncls, has_meta, to_start, nop, n_word_ranges, table_bytes;
+  uint32_t first_acc, first_leaf, acc0; // state numbering (pattern_host.hpp); acc0: the start state accepts
   uint32_t pin_a[8], pin_b[8], cbk[8], fst[8]; // 256-bit sets
   uint8_t chr[256];
   const uint8_t* cls;      // [256] byte -> class
@@ -35,6 +37,7 @@ struct DevPattern {
   const uint8_t* pred;     // [4096] pma_ when min < 4, else pmh_
   const uint8_t* tap;      // [2048]
   const int* word_ranges;  // [2 * n_word_ranges]
+  FilterPlan plan;         // first-stage filter of the position-parallel kernels
 };
 
 // the tables a kernel actually reads (shared-memory copies when staged, else the global ones)

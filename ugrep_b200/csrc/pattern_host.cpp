@@ -179,6 +179,38 @@ int flatten_dfa(const uint32_t* opc, uint32_t nop, HostDfa& out, std::string& er
   }
   const uint32_t ns = static_cast<uint32_t>(word_of.size());
   states.resize(ns);
+  // renumber: 0 = start | non-accepting with byte edges | accepting with byte edges | leaves (no byte edges).
+  // The scan kernels then test "accepting or leaf" with one compare against first_acc.
+  {
+    auto category = [&](uint32_t s) -> int {
+      bool edges = false;
+      for (uint32_t b = 0; b < 256 && !edges; ++b)
+        edges = states[s].target[b] != NONE;
+      return !edges ? 2 : states[s].accept != 0 ? 1 : 0;
+    };
+    std::vector<uint32_t> order; // new id -> old id
+    order.push_back(0);
+    uint32_t first[3] = {0, 0, 0};
+    for (int cat = 0; cat < 3; ++cat)
+    {
+      first[cat] = static_cast<uint32_t>(order.size());
+      for (uint32_t s = 1; s < ns; ++s)
+        if (category(s) == cat)
+          order.push_back(s);
+    }
+    out.first_acc = first[1];
+    out.first_leaf = first[2];
+    std::vector<RawState> st2(ns);
+    std::vector<uint32_t> w2(ns);
+    for (uint32_t i = 0; i < ns; ++i)
+    {
+      st2[i] = states[order[i]];
+      w2[i] = word_of[order[i]];
+      id_of[w2[i]] = i;
+    }
+    states.swap(st2);
+    word_of.swap(w2);
+  }
   // byte equivalence classes: bytes with identical columns
   std::map<std::vector<uint32_t>, uint32_t> col_id;
   uint32_t ncls = 0;
@@ -236,6 +268,249 @@ int flatten_dfa(const uint32_t* opc, uint32_t nop, HostDfa& out, std::string& er
   }
   out.meta_off[ns] = static_cast<uint32_t>(out.metas.size());
   return UGX_OK;
+}
+
+// ---- first-stage filter planning -------------------------------------------------------------------
+
+namespace {
+
+// a rough prior of byte frequencies in text (per mille), used only to rank filter choices
+double byte_prior(uint32_t c)
+{
+  static const double lower[26] = {65, 12, 22, 34, 102, 18, 16, 49, 56, 1, 6, 32, 19, 54, 60, 15, 1, 48, 51, 73, 22, 8, 19, 1, 16, 1};
+  if (c >= 'a' && c <= 'z')
+    return lower[c - 'a'];
+  if (c >= 'A' && c <= 'Z')
+    return lower[c - 'A'] * 0.05 + 0.5;
+  if (c == ' ')
+    return 150;
+  if (c >= '0' && c <= '9')
+    return 8;
+  if (c == '\n')
+    return 20;
+  if (c >= 0x80)
+    return 1.5;
+  if (c < 0x20 || c == 0x7f)
+    return 0.2;
+  return 3;
+}
+
+uint32_t to_ppm(double x)
+{
+  if (x < 0)
+    x = 0;
+  if (x > 1)
+    x = 1;
+  return static_cast<uint32_t>(x * 1e6);
+}
+
+// pass-rate estimate of a set of bytes under the prior
+double set_prior(const uint8_t* chars, uint32_t n)
+{
+  bool seen[256] = {false};
+  double s = 0;
+  for (uint32_t i = 0; i < n; ++i)
+    if (!seen[chars[i]])
+    {
+      seen[chars[i]] = true;
+      s += byte_prior(chars[i]);
+    }
+  return s / 1000.0;
+}
+
+// fraction of a predictor table's entries that have `bit` clear (a random hash index passes that often)
+double table_density(const uint8_t* tab, uint32_t size, uint32_t bit)
+{
+  uint32_t n = 0;
+  for (uint32_t i = 0; i < size; ++i)
+    n += ((tab[i] >> bit) & 1u) == 0;
+  return static_cast<double>(n) / size;
+}
+
+void lut_range(FilterPlan& plan)
+{
+  uint32_t lo = 24, hi = 0;
+  for (uint32_t t = 0; t < plan.nterms; ++t)
+  {
+    if (plan.t_off[t] < lo)
+      lo = plan.t_off[t];
+    if (plan.t_off[t] + 16 > hi)
+      hi = plan.t_off[t] + 16;
+  }
+  plan.p_lo = lo;
+  plan.p_hi = hi;
+}
+
+} // namespace
+
+void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan)
+{
+  memset(&plan, 0, sizeof(plan));
+  plan.kind = FK_ALL;
+  plan.est_pass_ppm = 1000000;
+  const uint8_t* pred = pf.min < 4 ? pf.pma : pf.pmh;
+  // where the predictor looks relative to the candidate position
+  uint32_t pm_shift = 0;
+  switch (adv)
+  {
+    case UGX_ADV_STRING:
+    case UGX_ADV_STRING_PMA:
+    case UGX_ADV_STRING_PMH:
+    {
+      // two rarest bytes of the literal within the first 9 positions
+      const uint32_t span = pf.len < 9 ? pf.len : 9;
+      uint32_t best[2] = {0, span > 1 ? 1u : 0u};
+      double score[2] = {1e9, 1e9};
+      for (uint32_t i = 0; i < span; ++i)
+      {
+        const double f = byte_prior(pf.chr[i]);
+        if (f < score[0])
+        {
+          score[1] = score[0];
+          best[1] = best[0];
+          score[0] = f;
+          best[0] = i;
+        }
+        else if (f < score[1])
+        {
+          score[1] = f;
+          best[1] = i;
+        }
+      }
+      if (span == 1)
+        best[1] = best[0];
+      plan.kind = FK_ANCHOR2;
+      for (int a = 0; a < 2; ++a)
+      {
+        plan.a_off[a] = best[a];
+        plan.a_chr[a] = pf.chr[best[a]] * 0x01010101u;
+      }
+      plan.est_pass_ppm = to_ppm(score[0] / 1000.0 * (span > 1 ? score[1] / 1000.0 : 1.0));
+      return;
+    }
+    case UGX_ADV_CHAR:
+    case UGX_ADV_CHAR_PMA:
+    case UGX_ADV_CHAR_PMH:
+      plan.kind = FK_LUT;
+      plan.hk = HK_BYTE;
+      memset(plan.fb, 0xff, 256);
+      plan.fb[pf.chr[0]] = 0;
+      plan.nterms = 1;
+      plan.t_off[0] = 0;
+      plan.t_bit[0] = 0;
+      plan.est_pass_ppm = to_ppm(byte_prior(pf.chr[0]) / 1000.0);
+      lut_range(plan);
+      return;
+    case UGX_ADV_PIN1_ONE:
+    case UGX_ADV_PIN_ONE:
+      plan.kind = FK_LUT;
+      plan.hk = HK_BYTE;
+      memset(plan.fb, 0xff, 256);
+      for (uint32_t i = 0; i < pf.pin; ++i)
+        plan.fb[pf.chr[i]] = 0;
+      plan.nterms = 1;
+      plan.est_pass_ppm = to_ppm(set_prior(pf.chr, pf.pin));
+      lut_range(plan);
+      return;
+    case UGX_ADV_PIN1_PMA:
+    case UGX_ADV_PIN1_PMH:
+    case UGX_ADV_PIN_PMA:
+    case UGX_ADV_PIN_PMH:
+    {
+      const double pins = set_prior(pf.chr, pf.pin) * (pf.lcs != pf.lcp ? set_prior(pf.chr + pf.pin, pf.pin) : 1.0);
+      double tail = 1.0;
+      if (pf.min >= 4)
+        for (uint32_t j = 3; j < pf.min; ++j)
+          tail *= table_density(pf.pmh, UGX_HASH, j);
+      if (pf.min >= 4 && tail < pins)
+      {
+        // hashed-predictor steps j >= 3 all read the same 4-byte rolling hash: one lookup per byte
+        plan.kind = FK_LUT;
+        plan.hk = HK_H4;
+        for (uint32_t j = 3; j < pf.min && plan.nterms < FILTER_MAX_TERMS; ++j)
+        {
+          plan.t_off[plan.nterms] = j;
+          plan.t_bit[plan.nterms] = j;
+          ++plan.nterms;
+        }
+        plan.est_pass_ppm = to_ppm(tail);
+      }
+      else
+      {
+        plan.kind = FK_LUT;
+        plan.hk = HK_BYTE;
+        memset(plan.fb, 0xff, 256);
+        for (uint32_t i = 0; i < pf.pin; ++i)
+        {
+          plan.fb[pf.chr[i]] &= static_cast<uint8_t>(~1u);
+          plan.fb[pf.chr[pf.pin + i]] &= static_cast<uint8_t>(~2u);
+        }
+        plan.nterms = 2;
+        plan.t_off[0] = pf.lcp;
+        plan.t_bit[0] = 0;
+        plan.t_off[1] = pf.lcs;
+        plan.t_bit[1] = 1;
+        plan.est_pass_ppm = to_ppm(pins);
+      }
+      lut_range(plan);
+      return;
+    }
+    case UGX_ADV_MIN1:
+    case UGX_ADV_MIN2:
+    case UGX_ADV_MIN3:
+    case UGX_ADV_MIN4:
+    {
+      // bitap over hashed byte pairs: step j reads bit j of tap[pair(k + j)]
+      const uint32_t depth = pf.min < 1 ? 1 : pf.min;
+      plan.kind = FK_LUT;
+      plan.hk = HK_PAIR;
+      double est = 1.0;
+      for (uint32_t j = 0; j < depth && plan.nterms < FILTER_MAX_TERMS; ++j)
+      {
+        const double d = table_density(pf.tap, UGX_BTAP, j);
+        if (d == 0.0)
+        {
+          plan.kind = FK_NEVER; // no pair can pass step j: the routine never stops on an interior position
+          plan.nterms = 0;
+          plan.est_pass_ppm = 0;
+          return;
+        }
+        plan.t_off[plan.nterms] = j;
+        plan.t_bit[plan.nterms] = j;
+        ++plan.nterms;
+        est *= d;
+      }
+      plan.est_pass_ppm = to_ppm(est);
+      lut_range(plan);
+      return;
+    }
+    case UGX_ADV_PMA:
+    {
+      // predict_match PM4 (include/reflex/pattern.h:389-401) passes iff, with p7..p0 the gathered bits,
+      //   !p7 | (!p6 & (!p5 | (!p4 & (!p3 | (!p2 & !p1))))) | (!p5 & !p3 & !p1 & !p0).
+      // A byte c0 can start a passing window only if !p7, or !p6, or some second byte gives !p5.
+      plan.kind = FK_LUT;
+      plan.hk = HK_BYTE;
+      double est = 0;
+      for (uint32_t c0 = 0; c0 < 256; ++c0)
+      {
+        bool ok = (pred[c0] & 0xc0) != 0xc0;
+        for (uint32_t c1 = 0; c1 < 256 && !ok; ++c1)
+          ok = (pred[((c0 << 3) ^ c1) & (UGX_HASH - 1)] & 0x20) == 0;
+        plan.fb[c0] = ok ? 0 : 0xff;
+        if (ok)
+          est += byte_prior(c0) / 1000.0;
+      }
+      plan.nterms = 1;
+      plan.t_off[0] = pm_shift;
+      plan.t_bit[0] = 0;
+      plan.est_pass_ppm = to_ppm(est);
+      lut_range(plan);
+      return;
+    }
+    default:
+      return;
+  }
 }
 
 int check_scope(const HostDfa& dfa, const ugx_prefilter& pf, uint32_t matcher_flags, std::string& err)

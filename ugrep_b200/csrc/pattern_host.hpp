@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/ugrep_b200.h"
+#include "filter_plan.hpp"
 
 namespace ugx {
 
@@ -36,6 +37,10 @@ struct HostDfa {
   bool has_meta = false;
   bool newline_live = false;       // some state has a transition on '\n'
   bool to_start = false;           // some transition targets state 0 (start-loop skip, lib/matcher.cpp:504-527)
+  // states are numbered: 0 = start, then non-accepting states with byte edges, then accepting states with
+  // byte edges, then states without byte edges ("leaves": the interpreter halts there before reading)
+  uint32_t first_acc = 0;          // ids >= first_acc (other than 0) are accepting or leaves
+  uint32_t first_leaf = 0;         // ids >= first_leaf (other than 0) are leaves
   uint32_t table_bytes() const { return nstates * ncls * 2; }
 };
 
@@ -44,6 +49,9 @@ int select_advance(const ugx_prefilter& pf, uint32_t matcher_flags);
 
 // returns UGX_OK or an error status; err receives a message
 int flatten_dfa(const uint32_t* opc, uint32_t nop, HostDfa& out, std::string& err);
+
+// first-stage filter of the position-parallel kernels (filter_plan.hpp)
+void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan);
 
 // checks that make the line-parallel scan exact for this pattern (DESIGN.md "line locality")
 int check_scope(const HostDfa& dfa, const ugx_prefilter& pf, uint32_t matcher_flags, std::string& err);
