@@ -141,3 +141,67 @@ def test_config_vs_reference_cli(gpu, name, cli):
     got = run_mode(api, sc, pat, data, mode)
     mine = O.format_list(data, got) if mode == "list" else b"%d\n" % got
     assert mine == ref
+
+
+# ---- every committed golden case (made with the unmodified reference), through every kernel route ----
+import golden_lib as G  # noqa: E402
+
+ROUTES = {"default": {}, "generic": {"force_generic": 1}, "legacy_any": {"legacy_any": 1},
+          "stream_nl": {"count_newlines": 1}}
+
+
+@pytest.mark.parametrize("route", list(ROUTES))
+@pytest.mark.parametrize("name", G.pattern_names())
+def test_golden_cases(gpu, name, route):
+    api, _ = gpu
+    sc = api.Scanner(0)
+    for k, v in ROUTES[route].items():
+        sc.set_option(k, v)
+    try:
+        pat = api.Pattern.load(G.pattern_path(name), 0)
+    except api.UgxError as ex:
+        assert ex.code == 2, ex  # UGX_E_UNSUPPORTED: outside the path's scope, rejected loudly
+        pytest.skip("out of scope: %s" % ex)
+    for case, data in G.cases(name):
+        t = sc.count_lines(pat, data)
+        assert t.matches == case["lines"], (name, route, case["input"], "lines")
+        if route == "stream_nl" and t.newlines:
+            assert t.newlines == data.count(b"\n"), (name, case["input"], "newlines")
+        if route in ("default", "generic"):
+            assert sc.count_matches(pat, data).matches == case["matches"], (name, route, case["input"], "matches")
+        if route == "default":
+            rec, _ = sc.find_all(pat, data)
+            assert len(rec) == case["matches"]
+            G.check_list(case, data, rec)
+
+
+def test_stream_count_ragged_and_chained(gpu):
+    """the streaming count at every length around chunk / span / block / region boundaries, with newlines placed
+    so that lines straddle regions and whole regions hold no newline"""
+    api, sc = gpu
+    sc2 = api.Scanner(0)
+    sc2.set_option("count_newlines", 1)
+    rng = np.random.default_rng(5)
+    for pname in ("c1", "c2", "c4", "w_the"):
+        path = os.path.join(PAT_DIR, pname + ".ugxp") if pname.startswith("c") else G.pattern_path(pname)
+        pat = api.Pattern.load(path, 0)
+        op = O.OraclePattern(path)
+        base = corpus.block("c4" if pname == "c4" else "c1", 100000).copy()
+        lit = b"Sherlock Holmes" if pname == "c1" else None
+        # long lines: drop most newlines, then sprinkle a few so that some 16 KiB regions have none
+        nl = np.flatnonzero(base == 10)
+        drop = nl[rng.random(len(nl)) < 0.97]
+        long_lines = base.copy()
+        long_lines[drop] = ord(" ")
+        if lit is not None:
+            for at in (5, 16370, 16384 - 7, 32768 + 100, 49152 - 15, 65536 - 1, 70000):
+                long_lines[at:at + len(lit)] = np.frombuffer(lit, dtype=np.uint8)
+                base[at:at + len(lit)] = np.frombuffer(lit, dtype=np.uint8)
+        for src in (base, long_lines):
+            for n in list(range(0, 70)) + [511, 512, 513, 2047, 2048, 2049, 2055, 2056, 2057, 16383, 16384, 16385,
+                                           16391, 16392, 16393, 32768, 49152 + 17, 65535, 65536, 65537, 99999, len(src)]:
+                data = src[:n]
+                want = op.count_lines(data)
+                assert sc.count_lines(pat, data).matches == want, (pname, n)
+                t = sc2.count_lines(pat, data)
+                assert t.matches == want and t.newlines == int((data == 10).sum()), (pname, n, "nl")

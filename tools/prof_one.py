@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--gib", type=float, default=1.0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--generic", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="scanner option name=value")
     a = ap.parse_args()
     pname, cname, mode = CFG[a.config]
     block = corpus.block(cname, 64 << 20)
@@ -32,6 +33,9 @@ def main():
     sc = api.Scanner(0, torch.cuda.current_stream().cuda_stream)
     if a.generic:
         sc.set_option("force_generic", 1)
+    for o in a.opt:
+        k, v = o.split("=")
+        sc.set_option(k, int(v))
     best = None
     for _ in range(a.reps):
         if mode == "lines":

@@ -12,11 +12,12 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libugrep_b200.so")
-SOURCES = ["capi.cu", "scan_kernels.cu", "fast_kernels.cu", "pattern_host.cpp"]
+SOURCES = ["capi.cu", "scan_kernels.cu", "fast_kernels.cu", "stream_count.cu", "pattern_host.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -39,18 +40,41 @@ def newest_source() -> float:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest_source():
         return LIB
-    cmd = [nvcc(), "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-O2,-Wall", "-shared",
-           "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-lcudart"]
+    # one nvcc per translation unit, in parallel (objects under build/, git-ignored), then one link
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = ["-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-O2,-Wall"]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
+        flags += ["-Xptxas", "-v"]
+
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp", ".h", ".inc"))]
+    headers.append(os.path.join(HERE, "..", "include", "ugrep_b200.h"))
+    headers.append(os.path.abspath(__file__))
+    hdr_time = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src: str):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + (".v.o" if verbose else ".o"))
+        if (not force and os.path.exists(obj)
+                and os.path.getmtime(obj) >= max(hdr_time, os.path.getmtime(os.path.join(CSRC, src)))):
+            return src, obj, subprocess.CompletedProcess([], 0, "", "(up to date)")
+        cmd = [nvcc(), *flags, "-c", "-o", obj, os.path.join(CSRC, src)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, r
+
+    objs = []
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        for src, obj, r in ex.map(compile_one, SOURCES):
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed on " + src)
+            if verbose:
+                print("==", src)
+                print(r.stdout + r.stderr)
+            objs.append(obj)
+    r = subprocess.run([nvcc(), *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed")
-    if verbose:
-        print(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
     return LIB
 
 

@@ -106,6 +106,13 @@ struct ugx_scanner {
   uint64_t records_n = 0;
   uint8_t* stage = nullptr; // device copy of a host buffer
   bool force_generic = false; // tests: always take the generic line-scan kernel
+  bool legacy_any = false;    // tests / A-B timing: the tile-synchronous count_lines_any kernel instead of the streaming one
+  bool count_newlines = false; // the streaming count also counts newlines
+  // streaming count scratch
+  uint8_t* region_sum = nullptr;
+  uint64_t region_cap = 0;
+  unsigned long long* partials = nullptr; // [2 * STREAM_MAX_GRID]
+  unsigned long long* ticket = nullptr;   // {ticket (u64), done (u32)}
   uint64_t stage_cap = 0;
 };
 
@@ -288,6 +295,12 @@ int ugx_scanner_create(int device, void* stream, ugx_scanner** out)
     e = cudaMalloc(reinterpret_cast<void**>(&s->totals), 4 * sizeof(unsigned long long));
   if (e == cudaSuccess)
     e = cudaMallocHost(reinterpret_cast<void**>(&s->h_totals), 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess)
+    e = cudaMalloc(reinterpret_cast<void**>(&s->partials), 2 * ugx::STREAM_MAX_GRID * sizeof(unsigned long long));
+  if (e == cudaSuccess)
+    e = cudaMalloc(reinterpret_cast<void**>(&s->ticket), 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess)
+    e = cudaMemset(s->ticket, 0, 2 * sizeof(unsigned long long));
   if (e != cudaSuccess)
   {
     ugx_scanner_destroy(s);
@@ -308,6 +321,9 @@ void ugx_scanner_destroy(ugx_scanner* s)
   cudaFree(s->strip_counts);
   cudaFree(s->totals);
   cudaFreeHost(s->h_totals);
+  cudaFree(s->region_sum);
+  cudaFree(s->partials);
+  cudaFree(s->ticket);
   cudaFree(s->records);
   cudaFree(s->stage);
   if (s->ev0)
@@ -423,7 +439,25 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
   a.base_offset = base_offset;
   a.base_line = base_line;
   CU(cudaEventRecord(s->ev0, s->stream));
-  if (mode == 0 && !want_records && !s->force_generic && ugx::count_lines_any_eligible(p->dev))
+  if (mode == 0 && !want_records && !s->force_generic && !s->legacy_any && ugx::count_lines_stream_eligible(p->dev))
+  {
+    rc = ensure(s->region_sum, s->region_cap, ugx::stream_regions(n) + 64);
+    if (rc != UGX_OK)
+      return rc;
+    ugx::StreamArgs sa;
+    sa.region_sum = s->region_sum;
+    sa.first_region = 0;
+    sa.partials = s->partials;
+    sa.ticket = s->ticket;
+    sa.done = reinterpret_cast<unsigned int*>(s->ticket + 1);
+    sa.totals = s->totals;
+    sa.finalize = 1;
+    sa.accumulate = 0;
+    sa.stage_table = 0;
+    CU(ugx::launch_count_lines_stream(p->dev, dbuf, n, sa, s->count_newlines, s->sm_count, s->stream, nullptr));
+    tt.launches = 1;
+  }
+  else if (mode == 0 && !want_records && !s->force_generic && ugx::count_lines_any_eligible(p->dev))
   {
     CU(ugx::launch_count_lines_any(p->dev, dbuf, n, s->totals, s->sm_count, s->stream));
     tt.launches = 1;
@@ -516,6 +550,16 @@ int ugx_scanner_set_option(ugx_scanner* s, const char* name, int value)
   if (strcmp(name, "force_generic") == 0)
   {
     s->force_generic = value != 0;
+    return UGX_OK;
+  }
+  if (strcmp(name, "legacy_any") == 0)
+  {
+    s->legacy_any = value != 0;
+    return UGX_OK;
+  }
+  if (strcmp(name, "count_newlines") == 0)
+  {
+    s->count_newlines = value != 0;
     return UGX_OK;
   }
   return fail(UGX_E_INVALID, std::string("unknown scanner option ") + name);

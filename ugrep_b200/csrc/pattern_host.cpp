@@ -357,28 +357,21 @@ void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan)
     case UGX_ADV_STRING_PMA:
     case UGX_ADV_STRING_PMH:
     {
-      // two rarest bytes of the literal within the first 9 positions
+      // anchor 0 is the first byte (compared without a shift), anchor 1 the rarest of bytes 1..8
       const uint32_t span = pf.len < 9 ? pf.len : 9;
-      uint32_t best[2] = {0, span > 1 ? 1u : 0u};
-      double score[2] = {1e9, 1e9};
-      for (uint32_t i = 0; i < span; ++i)
+      uint32_t best[2] = {0, 0};
+      double score[2] = {byte_prior(pf.chr[0]), 1e9};
+      for (uint32_t i = 1; i < span; ++i)
       {
         const double f = byte_prior(pf.chr[i]);
-        if (f < score[0])
-        {
-          score[1] = score[0];
-          best[1] = best[0];
-          score[0] = f;
-          best[0] = i;
-        }
-        else if (f < score[1])
+        if (f < score[1])
         {
           score[1] = f;
           best[1] = i;
         }
       }
       if (span == 1)
-        best[1] = best[0];
+        score[1] = 1000.0;
       plan.kind = FK_ANCHOR2;
       for (int a = 0; a < 2; ++a)
       {

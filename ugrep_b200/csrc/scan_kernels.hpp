@@ -34,6 +34,28 @@ cudaError_t launch_scan_lines(const DevPattern& P, const ScanArgs& a, int mode, 
 bool count_lines_any_eligible(const DevPattern& P);
 cudaError_t launch_count_lines_any(const DevPattern& P, const uint8_t* buf, uint64_t n, unsigned long long* totals,
                                    int sm_count, cudaStream_t st);
+// ---- streaming `ugrep -c` (stream_count.cu) ----
+constexpr int STREAM_THREADS = 256;                    // threads per CTA
+constexpr uint32_t SC_REGION = 16384;                  // bytes per region (unit of the ticket counter and of the summaries)
+constexpr uint32_t STREAM_MAX_GRID = 4096;             // capacity of the per-CTA partials
+
+struct StreamArgs {
+  uint8_t* region_sum;            // [first_region + regions(n) + 16] one summary byte per region
+  uint64_t first_region;          // index of this launch's first region within the whole buffer
+  unsigned long long* partials;   // [2 * STREAM_MAX_GRID] per-CTA {lines, newlines}
+  unsigned long long* ticket;     // region ticket counter (zero between launches)
+  unsigned int* done;             // finished-CTA counter (zero between launches)
+  unsigned long long* totals;     // [2] {matching lines, newlines}
+  uint32_t finalize;              // last launch of a buffer: chain the regions' head lines
+  uint32_t accumulate;            // add to totals instead of overwriting them
+  uint32_t stage_table;           // set by the launcher
+};
+
+bool count_lines_stream_eligible(const DevPattern& P);
+uint64_t stream_regions(uint64_t n);
+cudaError_t launch_count_lines_stream(const DevPattern& P, const uint8_t* buf, uint64_t n, StreamArgs a, bool want_nl,
+                                      int sm_count, cudaStream_t st, int* grid_out);
+
 cudaError_t launch_tile_prefix(uint64_t* tile_matches, uint64_t* tile_newlines, uint64_t ntiles,
                                unsigned long long* totals, cudaStream_t st);
 
