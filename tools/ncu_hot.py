@@ -20,7 +20,7 @@ def main():
     rep, kern = sys.argv[1], sys.argv[2]
     cub = sys.argv[3] if len(sys.argv) > 3 else "fast_kernels"
     d = tempfile.mkdtemp()
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "ugrep_b200", "libugrep_b200.so")], cwd=d,
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(os.environ.get("UGX_LIB") or os.path.join(ROOT, "ugrep_b200", "libugrep_b200.so"))], cwd=d,
                    capture_output=True)
     cubin = [f for f in os.listdir(d) if f.startswith(cub + ".")][0]
     dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cubin)], capture_output=True, text=True).stdout

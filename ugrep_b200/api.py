@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libugrep_b200.so")
+LIB_PATH = os.environ.get("UGX_LIB") or os.path.join(HERE, "libugrep_b200.so")  # UGX_LIB: A/B builds (tools/variants.py)
 
 MATCH_DTYPE = np.dtype([("line", "<u8"), ("offset", "<u8"), ("len", "<u4"), ("cap", "<u4")])
 

@@ -357,14 +357,17 @@ void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan)
     case UGX_ADV_STRING_PMA:
     case UGX_ADV_STRING_PMH:
     {
-      // anchor 0 is the first byte (compared without a shift), anchor 1 the rarest of bytes 1..8
-      const uint32_t span = pf.len < 9 ? pf.len : 9;
+      // anchor 0 is the first byte (compared without a shift).  Anchor 1 comes from bytes 1..12 (the register
+      // window holds 12 halo bytes): the farthest word-aligned offset (12, 8, 4: no funnel shift, and far from
+      // anchor 0, so less correlated with it) whose pair is selective enough under the byte prior, else the
+      // rarest byte (ties: the farthest).
+      const uint32_t span = pf.len < 13 ? pf.len : 13;
       uint32_t best[2] = {0, 0};
       double score[2] = {byte_prior(pf.chr[0]), 1e9};
       for (uint32_t i = 1; i < span; ++i)
       {
         const double f = byte_prior(pf.chr[i]);
-        if (f < score[1])
+        if (f <= score[1])
         {
           score[1] = f;
           best[1] = i;
@@ -372,6 +375,18 @@ void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan)
       }
       if (span == 1)
         score[1] = 1000.0;
+      for (uint32_t i = 12; i >= 4; i -= 4)
+      {
+        if (i >= span)
+          continue;
+        const double f = byte_prior(pf.chr[i]);
+        if (score[0] * f / 1e6 <= 2e-4 || f <= 1.5 * score[1])
+        {
+          score[1] = f;
+          best[1] = i;
+          break;
+        }
+      }
       plan.kind = FK_ANCHOR2;
       for (int a = 0; a < 2; ++a)
       {

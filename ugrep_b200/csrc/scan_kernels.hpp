@@ -35,8 +35,14 @@ bool count_lines_any_eligible(const DevPattern& P);
 cudaError_t launch_count_lines_any(const DevPattern& P, const uint8_t* buf, uint64_t n, unsigned long long* totals,
                                    int sm_count, cudaStream_t st);
 // ---- streaming `ugrep -c` (stream_count.cu) ----
-constexpr int STREAM_THREADS = 256;                    // threads per CTA
-constexpr uint32_t SC_REGION = 16384;                  // bytes per region (unit of the ticket counter and of the summaries)
+#ifndef UGX_STREAM_THREADS
+#define UGX_STREAM_THREADS 256
+#endif
+#ifndef UGX_SC_REGION
+#define UGX_SC_REGION 16384
+#endif
+constexpr int STREAM_THREADS = UGX_STREAM_THREADS;     // threads per CTA
+constexpr uint32_t SC_REGION = UGX_SC_REGION;                  // bytes per region (unit of the ticket counter and of the summaries)
 constexpr uint32_t STREAM_MAX_GRID = 4096;             // capacity of the per-CTA partials
 
 struct StreamArgs {
@@ -53,8 +59,13 @@ struct StreamArgs {
 
 bool count_lines_stream_eligible(const DevPattern& P);
 uint64_t stream_regions(uint64_t n);
+int stream_grid(uint64_t n, int sm_count, int per_sm);
 cudaError_t launch_count_lines_stream(const DevPattern& P, const uint8_t* buf, uint64_t n, StreamArgs a, bool want_nl,
-                                      int sm_count, cudaStream_t st, int* grid_out);
+                                      int sm_count, cudaStream_t st);
+// the literal specialisation (stream_literal.cu), taken by launch_count_lines_stream when eligible
+bool count_lines_literal_eligible(const DevPattern& P);
+cudaError_t launch_count_lines_literal(const DevPattern& P, const uint8_t* buf, uint64_t n, const StreamArgs& a, bool want_nl,
+                                       int sm_count, cudaStream_t st);
 
 cudaError_t launch_tile_prefix(uint64_t* tile_matches, uint64_t* tile_newlines, uint64_t ntiles,
                                unsigned long long* totals, cudaStream_t st);
