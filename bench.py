@@ -273,10 +273,9 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms = float(tm.item())
         # the one exchange step of the path: per-shard {matches, newlines} -> totals and line-number bases
-        mine = torch.tensor([tot.matches, tot.newlines], dtype=torch.int64, device="cuda")
-        allv = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
-        total_matches = int(sum(int(v[0]) for v in allv))
+        from ugrep_b200 import sharding
+        counts = sharding.all_gather_counts(tot.matches, tot.newlines, device="cuda")
+        total_matches = sum(c[0] for c in counts)
     else:
         total_matches = tot.matches
     ms_per_step = ms / args.steps

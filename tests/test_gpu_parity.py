@@ -147,7 +147,7 @@ def test_config_vs_reference_cli(gpu, name, cli):
 import golden_lib as G  # noqa: E402
 
 ROUTES = {"default": {}, "generic": {"force_generic": 1}, "legacy_any": {"legacy_any": 1},
-          "stream_nl": {"count_newlines": 1}}
+          "stream": {"stream_dfa": 1}, "stream_nl": {"stream_dfa": 1, "count_newlines": 1}}
 
 
 @pytest.mark.parametrize("route", list(ROUTES))
@@ -179,7 +179,9 @@ def test_stream_count_ragged_and_chained(gpu):
     """the streaming count at every length around chunk / span / block / region boundaries, with newlines placed
     so that lines straddle regions and whole regions hold no newline"""
     api, sc = gpu
+    sc.set_option("stream_dfa", 1)
     sc2 = api.Scanner(0)
+    sc2.set_option("stream_dfa", 1)
     sc2.set_option("count_newlines", 1)
     rng = np.random.default_rng(5)
     for pname in ("c1", "c2", "c4", "w_the"):
@@ -205,3 +207,4 @@ def test_stream_count_ragged_and_chained(gpu):
                 assert sc.count_lines(pat, data).matches == want, (pname, n)
                 t = sc2.count_lines(pat, data)
                 assert t.matches == want and t.newlines == int((data == 10).sum()), (pname, n, "nl")
+    sc.set_option("stream_dfa", 0)

@@ -108,6 +108,7 @@ struct ugx_scanner {
   bool force_generic = false; // tests: always take the generic line-scan kernel
   bool legacy_any = false;    // tests / A-B timing: the tile-synchronous count_lines_any kernel instead of the streaming one
   bool count_newlines = false; // the streaming count also counts newlines
+  bool stream_dfa = false;     // DFA patterns take the streaming count too (default: the tile-synchronous kernel)
   // streaming count scratch
   uint8_t* region_sum = nullptr;
   uint64_t region_cap = 0;
@@ -439,7 +440,8 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
   a.base_offset = base_offset;
   a.base_line = base_line;
   CU(cudaEventRecord(s->ev0, s->stream));
-  if (mode == 0 && !want_records && !s->force_generic && !s->legacy_any && ugx::count_lines_stream_eligible(p->dev))
+  if (mode == 0 && !want_records && !s->force_generic && !s->legacy_any && ugx::count_lines_stream_eligible(p->dev) &&
+      (s->stream_dfa || ugx::count_lines_literal_eligible(p->dev)))
   {
     rc = ensure(s->region_sum, s->region_cap, ugx::stream_regions(n) + 64);
     if (rc != UGX_OK)
@@ -555,6 +557,11 @@ int ugx_scanner_set_option(ugx_scanner* s, const char* name, int value)
   if (strcmp(name, "legacy_any") == 0)
   {
     s->legacy_any = value != 0;
+    return UGX_OK;
+  }
+  if (strcmp(name, "stream_dfa") == 0)
+  {
+    s->stream_dfa = value != 0;
     return UGX_OK;
   }
   if (strcmp(name, "count_newlines") == 0)

@@ -1,0 +1,52 @@
+"""Sharding of one corpus over the ranks of a job: line-aligned byte ranges, and the one
+exchange step of the path — an all-gather of per-shard {matches, newlines} from which every rank derives its
+record, line-number and byte-offset bases.  Host logic only; the backend is whatever torch.distributed was
+initialised with (NCCL on the GPU box, gloo in the CPU tests)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def line_aligned_cuts(data: np.ndarray, world: int) -> list[int]:
+    """world + 1 cut offsets: shard r is data[cuts[r]:cuts[r+1]]; every interior cut follows a newline, so a line
+    belongs to exactly one shard and no halo is needed."""
+    n = int(data.size)
+    cuts = [0]
+    for r in range(1, world):
+        target = max(cuts[-1], n * r // world)
+        if target >= n:
+            cuts.append(n)
+            continue
+        # forward to the end of the line that contains byte `target - 1` (or stay, if it ends right there)
+        if target == 0 or data[target - 1] == 10:
+            cuts.append(target)
+            continue
+        rel = np.flatnonzero(data[target:min(n, target + (1 << 20))] == 10)
+        if rel.size == 0:
+            rel = np.flatnonzero(data[target:] == 10)
+        cuts.append(target + int(rel[0]) + 1 if rel.size else n)
+    cuts.append(n)
+    return cuts
+
+
+def bases_from_counts(counts: list[tuple[int, int]], cuts: list[int]) -> list[tuple[int, int, int]]:
+    """per rank: (index of its first record in the global list, line-number base, byte-offset base)"""
+    out = []
+    m = nl = 0
+    for r, (matches, newlines) in enumerate(counts):
+        out.append((m, nl, cuts[r]))
+        m += matches
+        nl += newlines
+    return out
+
+
+def all_gather_counts(matches: int, newlines: int, device=None) -> list[tuple[int, int]]:
+    """the path's only collective: {matches, newlines} of every rank, in rank order"""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [(int(matches), int(newlines))]
+    mine = torch.tensor([int(matches), int(newlines)], dtype=torch.int64, device=device)
+    allv = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(allv, mine)
+    return [(int(v[0]), int(v[1])) for v in allv]
