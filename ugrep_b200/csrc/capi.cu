@@ -456,6 +456,7 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
     sa.finalize = 1;
     sa.accumulate = 0;
     sa.stage_table = 0;
+    sa.use_h4 = 0;
     CU(ugx::launch_count_lines_stream(p->dev, dbuf, n, sa, s->count_newlines, s->sm_count, s->stream));
     tt.launches = 1;
   }

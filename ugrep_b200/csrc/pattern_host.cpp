@@ -304,41 +304,37 @@ uint32_t to_ppm(double x)
   return static_cast<uint32_t>(x * 1e6);
 }
 
-// pass-rate estimate of a set of bytes under the prior
-double set_prior(const uint8_t* chars, uint32_t n)
+// necessary condition on the FIRST byte of a window for Pattern::predict_match to pass
+// (include/reflex/pattern.h:366-401): PMH step 0 reads bit 0 of pmh[c0]; PM4 passes iff, with p7..p0 the gathered
+// bits,  !p7 | (!p6 & (!p5 | ...)) | ...  — c0 can start a passing window only if !p7, or !p6, or some second byte
+// gives !p5.
+bool can_start(const ugx_prefilter& pf, uint32_t c0)
 {
-  bool seen[256] = {false};
-  double s = 0;
-  for (uint32_t i = 0; i < n; ++i)
-    if (!seen[chars[i]])
-    {
-      seen[chars[i]] = true;
-      s += byte_prior(chars[i]);
-    }
-  return s / 1000.0;
+  if (pf.min >= 4)
+    return (pf.pmh[c0] & 1u) == 0;
+  const uint8_t* pred = pf.pma;
+  if ((pred[c0] & 0xc0) != 0xc0)
+    return true;
+  for (uint32_t c1 = 0; c1 < 256; ++c1)
+    if ((pred[((c0 << 3) ^ c1) & (UGX_HASH - 1)] & 0x20) == 0)
+      return true;
+  return false;
 }
 
-// fraction of a predictor table's entries that have `bit` clear (a random hash index passes that often)
-double table_density(const uint8_t* tab, uint32_t size, uint32_t bit)
+// add a term: `in_set[c]` says whether byte c passes; returns the prior pass rate of the set
+double add_term(FilterPlan& plan, uint32_t off, const bool (&in_set)[256])
 {
-  uint32_t n = 0;
-  for (uint32_t i = 0; i < size; ++i)
-    n += ((tab[i] >> bit) & 1u) == 0;
-  return static_cast<double>(n) / size;
-}
-
-void lut_range(FilterPlan& plan)
-{
-  uint32_t lo = 24, hi = 0;
-  for (uint32_t t = 0; t < plan.nterms; ++t)
+  const uint32_t t = plan.nterms++;
+  plan.t_off[t] = off;
+  double pass = 0;
+  for (uint32_t c = 0; c < 256; ++c)
   {
-    if (plan.t_off[t] < lo)
-      lo = plan.t_off[t];
-    if (plan.t_off[t] + 16 > hi)
-      hi = plan.t_off[t] + 16;
+    if (in_set[c])
+      pass += byte_prior(c) / 1000.0;
+    else
+      plan.lut[c] |= 1u << (8 * t);
   }
-  plan.p_lo = lo;
-  plan.p_hi = hi;
+  return pass > 1.0 ? 1.0 : pass;
 }
 
 } // namespace
@@ -348,9 +344,12 @@ void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan)
   memset(&plan, 0, sizeof(plan));
   plan.kind = FK_ALL;
   plan.est_pass_ppm = 1000000;
-  const uint8_t* pred = pf.min < 4 ? pf.pma : pf.pmh;
-  // where the predictor looks relative to the candidate position
-  uint32_t pm_shift = 0;
+  // hashed-predictor terms: steps j >= 3 of predict_match read pmh[g(k + j)] with g a hash of 4 text bytes only
+  if (pf.min >= 4 && (adv == UGX_ADV_PIN1_PMH || adv == UGX_ADV_PIN_PMH || adv == UGX_ADV_MIN4 || adv == UGX_ADV_CHAR_PMH))
+  {
+    plan.h4_terms = pf.min - 3 > 3 ? 3 : pf.min - 3;
+    plan.h4_shift = adv == UGX_ADV_CHAR_PMH ? 1 : 0;
+  }
   switch (adv)
   {
     case UGX_ADV_STRING:
@@ -387,6 +386,22 @@ void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan)
           break;
         }
       }
+      if (!pf.one || adv != UGX_ADV_STRING)
+      {
+        // literal prefix followed by more pattern: the same two bytes as byte-set terms
+        plan.kind = FK_LUT;
+        bool s0[256] = {false}, s1[256] = {false};
+        s0[pf.chr[0]] = true;
+        double est = add_term(plan, 0, s0);
+        if (span > 1)
+        {
+          uint32_t j = best[1] <= 8 ? best[1] : 1;
+          s1[pf.chr[j]] = true;
+          est *= add_term(plan, j, s1);
+        }
+        plan.est_pass_ppm = to_ppm(est);
+        return;
+      }
       plan.kind = FK_ANCHOR2;
       for (int a = 0; a < 2; ++a)
       {
@@ -399,68 +414,62 @@ void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan)
     case UGX_ADV_CHAR:
     case UGX_ADV_CHAR_PMA:
     case UGX_ADV_CHAR_PMH:
+    {
       plan.kind = FK_LUT;
-      plan.hk = HK_BYTE;
-      memset(plan.fb, 0xff, 256);
-      plan.fb[pf.chr[0]] = 0;
-      plan.nterms = 1;
-      plan.t_off[0] = 0;
-      plan.t_bit[0] = 0;
-      plan.est_pass_ppm = to_ppm(byte_prior(pf.chr[0]) / 1000.0);
-      lut_range(plan);
+      bool set0[256] = {false};
+      set0[pf.chr[0]] = true;
+      double est = add_term(plan, 0, set0);
+      if (adv != UGX_ADV_CHAR)
+      {
+        bool set1[256];
+        for (uint32_t c = 0; c < 256; ++c)
+          set1[c] = can_start(pf, c); // the predictor looks at k + 1
+        est *= add_term(plan, 1, set1);
+      }
+      plan.est_pass_ppm = to_ppm(est);
       return;
+    }
     case UGX_ADV_PIN1_ONE:
     case UGX_ADV_PIN_ONE:
+    {
+      // needle set at k, and the predictor's first-byte condition at the same byte
       plan.kind = FK_LUT;
-      plan.hk = HK_BYTE;
-      memset(plan.fb, 0xff, 256);
+      bool set0[256] = {false};
       for (uint32_t i = 0; i < pf.pin; ++i)
-        plan.fb[pf.chr[i]] = 0;
-      plan.nterms = 1;
-      plan.est_pass_ppm = to_ppm(set_prior(pf.chr, pf.pin));
-      lut_range(plan);
+        set0[pf.chr[i]] = true;
+      for (uint32_t c = 0; c < 256; ++c)
+        set0[c] = set0[c] && can_start(pf, c);
+      plan.est_pass_ppm = to_ppm(add_term(plan, 0, set0));
       return;
+    }
     case UGX_ADV_PIN1_PMA:
     case UGX_ADV_PIN1_PMH:
     case UGX_ADV_PIN_PMA:
     case UGX_ADV_PIN_PMH:
     {
-      const double pins = set_prior(pf.chr, pf.pin) * (pf.lcs != pf.lcp ? set_prior(pf.chr + pf.pin, pf.pin) : 1.0);
-      double tail = 1.0;
-      if (pf.min >= 4)
-        for (uint32_t j = 3; j < pf.min; ++j)
-          tail *= table_density(pf.pmh, UGX_HASH, j);
-      if (pf.min >= 4 && tail < pins)
+      // needle sets at k + lcp and k + lcs, and the predictor's first-byte condition at k
+      plan.kind = FK_LUT;
+      bool seta[256] = {false}, setb[256] = {false}, setz[256];
+      for (uint32_t i = 0; i < pf.pin; ++i)
       {
-        // hashed-predictor steps j >= 3 all read the same 4-byte rolling hash: one lookup per byte
-        plan.kind = FK_LUT;
-        plan.hk = HK_H4;
-        for (uint32_t j = 3; j < pf.min && plan.nterms < FILTER_MAX_TERMS; ++j)
-        {
-          plan.t_off[plan.nterms] = j;
-          plan.t_bit[plan.nterms] = j;
-          ++plan.nterms;
-        }
-        plan.est_pass_ppm = to_ppm(tail);
+        seta[pf.chr[i]] = true;
+        setb[pf.chr[pf.pin + i]] = true;
       }
-      else
-      {
-        plan.kind = FK_LUT;
-        plan.hk = HK_BYTE;
-        memset(plan.fb, 0xff, 256);
-        for (uint32_t i = 0; i < pf.pin; ++i)
-        {
-          plan.fb[pf.chr[i]] &= static_cast<uint8_t>(~1u);
-          plan.fb[pf.chr[pf.pin + i]] &= static_cast<uint8_t>(~2u);
-        }
-        plan.nterms = 2;
-        plan.t_off[0] = pf.lcp;
-        plan.t_bit[0] = 0;
-        plan.t_off[1] = pf.lcs;
-        plan.t_bit[1] = 1;
-        plan.est_pass_ppm = to_ppm(pins);
-      }
-      lut_range(plan);
+      for (uint32_t c = 0; c < 256; ++c)
+        setz[c] = can_start(pf, c);
+      double est = 1.0;
+      if (pf.lcp == 0)
+        for (uint32_t c = 0; c < 256; ++c)
+          seta[c] = seta[c] && setz[c];
+      else if (pf.lcs == 0)
+        for (uint32_t c = 0; c < 256; ++c)
+          setb[c] = setb[c] && setz[c];
+      est *= add_term(plan, pf.lcp, seta);
+      if (pf.lcs != pf.lcp)
+        est *= add_term(plan, pf.lcs, setb);
+      if (pf.lcp != 0 && pf.lcs != 0)
+        est *= add_term(plan, 0, setz);
+      plan.est_pass_ppm = to_ppm(est);
       return;
     }
     case UGX_ADV_MIN1:
@@ -468,52 +477,32 @@ void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan)
     case UGX_ADV_MIN3:
     case UGX_ADV_MIN4:
     {
-      // bitap over hashed byte pairs: step j reads bit j of tap[pair(k + j)]
+      // bitap over hashed byte pairs: step j reads bit j of tap[pair(k + j)].  Byte-level necessary condition:
+      // byte (k + j) must be the first byte of SOME pair that passes step j.
       const uint32_t depth = pf.min < 1 ? 1 : pf.min;
       plan.kind = FK_LUT;
-      plan.hk = HK_PAIR;
       double est = 1.0;
       for (uint32_t j = 0; j < depth && plan.nterms < FILTER_MAX_TERMS; ++j)
       {
-        const double d = table_density(pf.tap, UGX_BTAP, j);
-        if (d == 0.0)
+        bool setj[256];
+        for (uint32_t c = 0; c < 256; ++c)
         {
-          plan.kind = FK_NEVER; // no pair can pass step j: the routine never stops on an interior position
-          plan.nterms = 0;
-          plan.est_pass_ppm = 0;
-          return;
+          setj[c] = false;
+          for (uint32_t d = 0; d < 256 && !setj[c]; ++d)
+            setj[c] = ((pf.tap[(c ^ (d << 6)) & (UGX_BTAP - 1)] >> j) & 1u) == 0;
         }
-        plan.t_off[plan.nterms] = j;
-        plan.t_bit[plan.nterms] = j;
-        ++plan.nterms;
-        est *= d;
+        est *= add_term(plan, j, setj);
       }
       plan.est_pass_ppm = to_ppm(est);
-      lut_range(plan);
       return;
     }
     case UGX_ADV_PMA:
     {
-      // predict_match PM4 (include/reflex/pattern.h:389-401) passes iff, with p7..p0 the gathered bits,
-      //   !p7 | (!p6 & (!p5 | (!p4 & (!p3 | (!p2 & !p1))))) | (!p5 & !p3 & !p1 & !p0).
-      // A byte c0 can start a passing window only if !p7, or !p6, or some second byte gives !p5.
       plan.kind = FK_LUT;
-      plan.hk = HK_BYTE;
-      double est = 0;
-      for (uint32_t c0 = 0; c0 < 256; ++c0)
-      {
-        bool ok = (pred[c0] & 0xc0) != 0xc0;
-        for (uint32_t c1 = 0; c1 < 256 && !ok; ++c1)
-          ok = (pred[((c0 << 3) ^ c1) & (UGX_HASH - 1)] & 0x20) == 0;
-        plan.fb[c0] = ok ? 0 : 0xff;
-        if (ok)
-          est += byte_prior(c0) / 1000.0;
-      }
-      plan.nterms = 1;
-      plan.t_off[0] = pm_shift;
-      plan.t_bit[0] = 0;
-      plan.est_pass_ppm = to_ppm(est);
-      lut_range(plan);
+      bool set0[256];
+      for (uint32_t c = 0; c < 256; ++c)
+        set0[c] = can_start(pf, c);
+      plan.est_pass_ppm = to_ppm(add_term(plan, 0, set0));
       return;
     }
     default:

@@ -75,7 +75,8 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
   uint8_t* s_tap = s_pred + UGX_HASH;
   uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_tap + UGX_BTAP);
   uint32_t* s_nl = s_cand + SCAN_TILE / 32;
-  uint16_t* s_next = reinterpret_cast<uint16_t*>(s_nl + SCAN_TILE / 32);
+  uint16_t* s_lines = reinterpret_cast<uint16_t*>(s_nl + SCAN_TILE / 32);
+  uint16_t* s_next = s_lines + SCAN_LINE_CAP;
   for (uint32_t i = threadIdx.x; i < 256 / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(s_cls)[i] = __ldg(reinterpret_cast<const uint32_t*>(P.cls) + i);
   for (uint32_t i = threadIdx.x; i < UGX_HASH / 16; i += blockDim.x)
@@ -124,53 +125,114 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
       line_no = tile_newlines[tile] + nlex + 1 + base_line;
     }
 
-    // ---- every line that starts in my strip ----
-    uint64_t rest = starts;
-    while (rest != 0)
+    // ---- lines -> threads.  Counting without records: the tile's line starts are compacted into shared memory
+    // and handed out densely (thread i takes lines i, i + 256, ...), so nearly every lane has a line to run; the
+    // strip-owner assignment (a thread runs the lines that start in its 64-byte strip) is kept for record
+    // passes, whose output offsets are per strip, and for tiles with more line starts than the list holds.
+    bool dense = false;
+    if (!EMIT && strip_counts == nullptr)
     {
-      const uint32_t bit = __ffsll(static_cast<long long>(rest)) - 1;
-      rest &= rest - 1;
-      const uint64_t L = s0 + bit;
-      // end of the line: its '\n', or the last byte of the buffer
-      uint64_t last;
+      uint32_t total_lines;
+      const uint32_t first_idx = block_excl_scan(static_cast<uint32_t>(__popcll(starts)), warp_sums, &total_lines);
+      if (total_lines <= SCAN_LINE_CAP)
       {
-        const uint64_t after = nl >> bit; // newlines at or after L inside the strip
-        if (after != 0)
-          last = L + (__ffsll(static_cast<long long>(after)) - 1);
-        else
+        dense = true;
+        uint32_t idx = first_idx;
+        uint64_t rest = starts;
+        while (rest != 0)
         {
-          uint64_t p = s0 + SCAN_STRIP;
-          while (p < n && __ldg(buf + p) != '\n')
-            ++p;
-          last = p < n ? p : n - 1;
+          const uint32_t bit = __ffsll(static_cast<long long>(rest)) - 1;
+          rest &= rest - 1;
+          s_lines[idx++] = static_cast<uint16_t>(threadIdx.x * SCAN_STRIP + bit);
         }
-      }
-      uint64_t this_line = 0;
-      if (EMIT)
-        this_line = line_no + __popcll(nl & ((1ull << bit) - 1));
-      Cursor m;
-      set_current(t, m, L);
-      for (;;)
-      {
-        uint32_t cap = find_in_line<HAS_META>(t, P, T, cm, m, last);
-        if (cap == 0)
-          break;
-        if (EMIT)
+        __syncthreads();
+        constexpr uint32_t NW = SCAN_TILE / 32;
+        for (uint32_t i = threadIdx.x; i < total_lines; i += blockDim.x)
         {
-          uint64_t idx = out_pos + strip_total;
-          if (idx < out_cap)
+          const uint32_t off = s_lines[i];
+          const uint64_t L = tile_base + off;
+          // end of the line: the next newline in the tile's bitmap, else walk on in global memory
+          uint64_t last;
           {
-            ugx_match r;
-            r.line = this_line;
-            r.offset = m.txt + base_offset;
-            r.len = m.len;
-            r.cap = cap;
-            out[idx] = r;
+            uint32_t wi = off >> 5;
+            uint32_t word = s_nl[wi] & (0xffffffffu << (off & 31));
+            while (word == 0 && ++wi < NW)
+              word = s_nl[wi];
+            if (word != 0)
+              last = tile_base + (wi << 5) + (__ffs(word) - 1);
+            else
+            {
+              uint64_t p = tile_base + SCAN_TILE;
+              while (p < n && __ldg(buf + p) != '\n')
+                ++p;
+              last = p < n ? p : n - 1;
+            }
+            if (last >= n)
+              last = n - 1;
+          }
+          Cursor m;
+          set_current(t, m, L);
+          for (;;)
+          {
+            if (find_in_line<HAS_META>(t, P, T, cm, m, last) == 0)
+              break;
+            ++strip_total;
+            if (MODE == 0)
+              break;
           }
         }
-        ++strip_total;
-        if (MODE == 0)
-          break;
+      }
+    }
+    if (!dense)
+    {
+      // ---- every line that starts in my strip ----
+      uint64_t rest = starts;
+      while (rest != 0)
+      {
+        const uint32_t bit = __ffsll(static_cast<long long>(rest)) - 1;
+        rest &= rest - 1;
+        const uint64_t L = s0 + bit;
+        // end of the line: its '\n', or the last byte of the buffer
+        uint64_t last;
+        {
+          const uint64_t after = nl >> bit; // newlines at or after L inside the strip
+          if (after != 0)
+            last = L + (__ffsll(static_cast<long long>(after)) - 1);
+          else
+          {
+            uint64_t p = s0 + SCAN_STRIP;
+            while (p < n && __ldg(buf + p) != '\n')
+              ++p;
+            last = p < n ? p : n - 1;
+          }
+        }
+        uint64_t this_line = 0;
+        if (EMIT)
+          this_line = line_no + __popcll(nl & ((1ull << bit) - 1));
+        Cursor m;
+        set_current(t, m, L);
+        for (;;)
+        {
+          uint32_t cap = find_in_line<HAS_META>(t, P, T, cm, m, last);
+          if (cap == 0)
+            break;
+          if (EMIT)
+          {
+            uint64_t idx = out_pos + strip_total;
+            if (idx < out_cap)
+            {
+              ugx_match r;
+              r.line = this_line;
+              r.offset = m.txt + base_offset;
+              r.len = m.len;
+              r.cap = cap;
+              out[idx] = r;
+            }
+          }
+          ++strip_total;
+          if (MODE == 0)
+            break;
+        }
       }
     }
 
@@ -258,7 +320,7 @@ tile_prefix_kernel(uint64_t* __restrict__ tile_matches, uint64_t* __restrict__ t
 
 static size_t scan_smem_bytes(const DevPattern& P, bool stage)
 {
-  return 256 + UGX_HASH + UGX_BTAP + 2 * (SCAN_TILE / 8) + (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
+  return 256 + UGX_HASH + UGX_BTAP + 2 * (SCAN_TILE / 8) + 2 * SCAN_LINE_CAP + (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
 }
 
 template <int MODE, bool EMIT, bool HAS_META>

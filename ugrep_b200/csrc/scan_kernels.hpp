@@ -13,6 +13,7 @@ struct DevPattern;
 constexpr int SCAN_THREADS = 256;                      // threads per CTA
 constexpr int SCAN_STRIP = 64;                         // bytes per thread per tile
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_STRIP;   // bytes per CTA iteration (16 KiB)
+constexpr uint32_t SCAN_LINE_CAP = 1024;                // line starts per tile the dense line list holds
 constexpr uint32_t SCAN_MAX_SMEM_TABLE = 200 * 1024;   // largest transition table staged in shared memory
 constexpr uint32_t ANY_TILE = 32768;                   // bytes per CTA iteration of count_lines_any_kernel
 
@@ -55,11 +56,12 @@ struct StreamArgs {
   uint32_t finalize;              // last launch of a buffer: chain the regions' head lines
   uint32_t accumulate;            // add to totals instead of overwriting them
   uint32_t stage_table;           // set by the launcher
+  uint32_t use_h4;                // set by the launcher: stage the hashed-predictor term table
 };
 
 bool count_lines_stream_eligible(const DevPattern& P);
 uint64_t stream_regions(uint64_t n);
-int stream_grid(uint64_t n, int sm_count, int per_sm);
+int stream_grid(uint64_t n, int sm_count, int per_sm, int threads);
 cudaError_t launch_count_lines_stream(const DevPattern& P, const uint8_t* buf, uint64_t n, StreamArgs a, bool want_nl,
                                       int sm_count, cudaStream_t st);
 // the literal specialisation (stream_literal.cu), taken by launch_count_lines_stream when eligible

@@ -133,9 +133,9 @@ __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes)
 __device__ __forceinline__ void stream_epilogue(const StreamArgs& a, uint64_t nregions, unsigned long long my_lines,
                                                 unsigned long long my_newlines, uint32_t warp_uniform_lines)
 {
-  __shared__ unsigned long long s_red[2 * (STREAM_THREADS / 32)];
+  __shared__ unsigned long long s_red[2 * 32];
   __shared__ uint32_t s_last;
-  __shared__ uint8_t s_slice[STREAM_THREADS];
+  __shared__ uint8_t s_slice[1024];
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0)
     my_lines += warp_uniform_lines;
@@ -310,7 +310,7 @@ __device__ __forceinline__ void stream_span(const uint32_t (&w)[7], uint64_t sba
 
 // one region.  FULL: the region, its halo and the first block of the warp's next region lie wholly inside the
 // buffer, so no load is guarded and no span is tested against the end of the buffer.
-template <bool FULL, bool WANT_NL, class Eval>
+template <bool FULL, bool WANT_NL, bool SPLIT_WATCH, class Eval>
 __device__ __forceinline__ void stream_region(const uint8_t* __restrict__ buf, uint64_t n, uint64_t rbase, bool have_next,
                                               uint64_t next_rbase, uint32_t lane, uint32_t next_lane, uint4 (&v)[SC_SPANS],
                                               uint4& h, LineState& L, unsigned long long& my_newlines, Eval& ev)
@@ -361,7 +361,8 @@ __device__ __forceinline__ void stream_region(const uint8_t* __restrict__ buf, u
         w[5] = __shfl_sync(0xffffffffu, lane == 0 ? nv.y : w[1], next_lane);
         w[6] = __shfl_sync(0xffffffffu, lane == 0 ? nv.z : w[2], next_lane);
         // two instantiations so that the cruising path (no newline watch) carries no newline code at all
-        if (WANT_NL || L.watch)
+        // (SPLIT_WATCH false: kernels whose span evaluation dwarfs the newline test keep one copy, for code size)
+        if (WANT_NL || !SPLIT_WATCH || L.watch)
           stream_span<true, WANT_NL>(w, sbase, L, nlacc, ev);
         else
           stream_span<false, WANT_NL>(w, sbase, L, nlacc, ev);
@@ -381,7 +382,7 @@ __device__ __forceinline__ void stream_region(const uint8_t* __restrict__ buf, u
   }
 }
 
-template <bool WANT_NL, class Eval>
+template <bool WANT_NL, bool SPLIT_WATCH, class Eval>
 __device__ __forceinline__ void stream_scan(const uint8_t* __restrict__ buf, uint64_t n, const StreamArgs& a, Eval& ev)
 {
   uint32_t lane = threadIdx.x & 31;
@@ -418,9 +419,9 @@ __device__ __forceinline__ void stream_scan(const uint8_t* __restrict__ buf, uin
     L.lcount = 0;
     const bool full = rbase + SC_REGION + 16 <= n && (!have_next || next_rbase + SC_BLOCK + 16 <= n);
     if (full)
-      stream_region<true, WANT_NL>(buf, n, rbase, have_next, next_rbase, lane, next_lane, v, h, L, my_newlines, ev);
+      stream_region<true, WANT_NL, SPLIT_WATCH>(buf, n, rbase, have_next, next_rbase, lane, next_lane, v, h, L, my_newlines, ev);
     else
-      stream_region<false, WANT_NL>(buf, n, rbase, have_next, next_rbase, lane, next_lane, v, h, L, my_newlines, ev);
+      stream_region<false, WANT_NL, SPLIT_WATCH>(buf, n, rbase, have_next, next_rbase, lane, next_lane, v, h, L, my_newlines, ev);
     // publish the region: bit 0 has newline, bit 1 head success, bit 2 carry out
     if (lane == 0)
     {

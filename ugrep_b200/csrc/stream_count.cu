@@ -82,60 +82,233 @@ __device__ __forceinline__ bool attempt_at(const Text& t, const DevPattern& P, c
   return attempt_meta(t, P, pos);
 }
 
-// candidates of the chunk by the reference's prefilter predicate, then one anchored attempt per candidate
+// stage 2 for one survivor: the exact candidate predicate, then one anchored attempt.  Not inlined: the span loop is
+// instantiated 16 times (4 spans x watch/cruise x full/guarded) and must stay within the instruction cache.
+// the needle + hashed-predictor routines on an interior position (pos + 12 <= end): the 8 bytes the predicate reads
+// come from three aligned 32-bit loads instead of eight guarded byte loads
+__device__ __forceinline__ bool cand_pin_pmh_interior(const Text& t, const DevPattern& P, const Tables& T, uint64_t pos)
+{
+  const uint8_t* p = t.b + pos;
+  const uint32_t sh = (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p)) & 3u) * 8;
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(p - (sh >> 3));
+  const uint32_t lo = __ldg(a), mid = __ldg(a + 1), hi = __ldg(a + 2);
+  const uint32_t x = __funnelshift_r(lo, mid, sh), y = __funnelshift_r(mid, hi, sh);
+  const uint64_t xy = (static_cast<uint64_t>(y) << 32) | x;
+  const uint32_t ca = static_cast<uint32_t>(xy >> (8 * P.lcp)) & 0xffu, cb = static_cast<uint32_t>(xy >> (8 * P.lcs)) & 0xffu;
+  if (P.adv == UGX_ADV_PIN1_PMH)
+  {
+    if (ca != P.chr[0] || cb != P.chr[1])
+      return false;
+  }
+  else if (!bit256(P.pin_a, ca) || !bit256(P.pin_b, cb))
+    return false;
+  return pmh_xy(T.pred, x, y, P.min);
+}
+
+template <int KIND>
+__device__ __noinline__ bool stage2(Text t, const DevPattern& P, Tables T, uint64_t pos, bool exact)
+{
+  if (!exact)
+  {
+    const bool pin_pmh = P.adv == UGX_ADV_PIN_PMH || P.adv == UGX_ADV_PIN1_PMH;
+    if (pin_pmh && pos + 12 <= t.end ? !cand_pin_pmh_interior(t, P, T, pos) : !cand(t, P, T, pos))
+      return false;
+  }
+  return attempt_at<KIND>(t, P, T, pos);
+}
+
+// exact per-position candidates of one chunk (families without a byte-set plan, spans near the end of the buffer)
+__device__ __noinline__ uint32_t exact_chunk_candidates(Text t, const DevPattern& P, Tables T, uint64_t base, uint32_t w0,
+                                                        uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5)
+{
+  if (base >= t.end)
+    return 0;
+  if (base + 24 > t.end)
+    return chunk_cand_generic(t, P, T, base);
+  Window W;
+  W.w[0] = w0;
+  W.w[1] = w1;
+  W.w[2] = w2;
+  W.w[3] = w3;
+  W.w[4] = w4;
+  W.w[5] = w5;
+  W.w[6] = 0;
+  return chunk_cand_fast(W, t, P, T, base);
+}
+
+// Span evaluation for DFA patterns, in three steps:
+//   1. survivors: the FilterPlan's byte-set terms (one shared-memory lookup per text byte, eight positions
+//      accumulated per register; the right halo's fail bits come from the next lane) — a superset of the
+//      reference's candidates.  Families without a byte-set plan, and spans near the end of the buffer, take the
+//      exact per-position predicate instead;
+//   2. the warp's survivors are compacted into a small shared-memory queue and handed out one per lane, so that
+//      all 32 lanes run stage 2 whatever the survivors' distribution over chunks;
+//   3. per survivor: the exact candidate predicate cand() (device_pattern.cuh) and one anchored DFA attempt.
 template <int KIND>
 struct DfaEval {
   const DevPattern& P;
   Tables T;
   Text t;
-  uint32_t lane;
+  uint32_t lane, next_lane;
+  const uint32_t* lut;  // [256] shared: bit 8*t set = the byte fails term t
+  const uint32_t* h4;   // [4096] shared: bit 8*t set = pmh[g] fails hashed-predictor step 3 + t; nullptr = unused
+  uint32_t h4_shift;
+  uint16_t* queue;      // [64] per warp
+  uint32_t* succ;       // [16] per warp: success bits of the span, bit (16 * lane + k)
+  uint32_t nterms, off0, off1, off2;
+  bool use_lut;
+
+  __device__ __forceinline__ void try_at(uint64_t sbase, uint32_t off, bool exact) const
+  {
+    if (stage2<KIND>(t, P, T, sbase + off, exact))
+      atomicOr(&succ[off >> 5], 1u << (off & 31));
+  }
 
   __device__ __forceinline__ bool operator()(const uint32_t (&w)[7], uint64_t sbase, uint32_t& succ16) const
   {
-    const uint64_t base = sbase + lane * 16;
-    uint32_t cm = 0;
-    if (base < t.end)
+    const bool interior = sbase + SC_SPAN + 24 <= t.end; // uniform
+    uint32_t surv = 0;
+    bool exact;
+    if (h4 != nullptr && interior)
     {
-      if (base + 24 <= t.end)
-      {
-        Window W;
+      // hashed-predictor terms: one rolling 12-bit hash and one lookup per text byte.  Byte i of the predictor
+      // window of position k is text byte k + h4_shift + i; c[] is the chunk shifted by h4_shift.
+      exact = false;
+      uint32_t c[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
-          W.w[i] = w[i];
-        W.w[6] = 0;
-        cm = chunk_cand_fast(W, t, P, T, base);
+      for (int i = 0; i < 6; ++i)
+        c[i] = __funnelshift_r(w[i], w[i + 1], 8 * h4_shift);
+      uint32_t g = 0, acc_a = 0, acc_b = 0, acc_c = 0;
+#pragma unroll
+      for (int p = 0; p <= 20; ++p)
+      {
+        const uint32_t byte = (c[p >> 2] >> (8 * (p & 3))) & 0xffu;
+        g = ((g << 3) ^ byte) & (UGX_HASH - 1);
+        if (p >= 3)
+        {
+          const uint32_t v = h4[g];
+          if (p <= 10)
+            acc_a = acc_a * 2 + v;
+          else if (p <= 18)
+            acc_b = acc_b * 2 + v;
+          else
+            acc_c = acc_c * 2 + v;
+        }
       }
-      else
-        cm = chunk_cand_generic(t, P, T, base);
+      // acc_a: p = 3..10 (first at bit 7 of each plane byte), acc_b: p = 11..18, acc_c: p = 19, 20 (bits 1, 0).
+      // Bit-reverse: plane t moves to byte 3 - t with p ascending from its bit 0.
+      const uint32_t ra = __brev(acc_a), rb = __brev(acc_b), rc = __brev(acc_c << 6);
+      // step 3 + t at position k reads p = k + 3 + t
+      uint32_t fail = (ra >> 24) | ((rb >> 24) << 8);                                              // t = 0: k = p - 3
+      fail |= (((ra >> 16) & 0xffu) >> 1) | (((rb >> 16) & 0xffu) << 7) | (((rc >> 16) & 1u) << 15); // t = 1: k = p - 4
+      fail |= (((ra >> 8) & 0xffu) >> 2) | (((rb >> 8) & 0xffu) << 6) | (((rc >> 8) & 3u) << 14);    // t = 2: k = p - 5
+      surv = ~fail & 0xffffu;
     }
-    while (cm != 0)
+    else if (use_lut && interior)
     {
-      const uint32_t k = __ffs(cm) - 1;
-      cm &= cm - 1;
-      if (attempt_at<KIND>(t, P, T, base + k))
-        succ16 |= 1u << k;
+      exact = false;
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int k = 7; k >= 0; --k)
+      {
+        lo = lo * 2 + lut[(w[k >> 2] >> (8 * (k & 3))) & 0xffu];
+        hi = hi * 2 + lut[(w[2 + (k >> 2)] >> (8 * (k & 3))) & 0xffu];
+      }
+      // fail masks of this chunk: f01 = term 0 (bits 0-15) | term 1 (bits 16-31), f2 = term 2
+      const uint32_t f01 = __byte_perm(lo, hi, 0x5140);
+      const uint32_t f2 = __byte_perm(lo, hi, 0x4462) & 0xffffu;
+      uint32_t n01 = __shfl_sync(0xffffffffu, f01, next_lane);
+      uint32_t n2 = nterms > 2 ? __shfl_sync(0xffffffffu, f2, next_lane) : 0u;
+      if (lane == 31)
+      {
+        // the next span's first chunk is not evaluated yet: let its positions pass (stage 2 is exact)
+        n01 = 0;
+        n2 = 0;
+      }
+      uint32_t fail = ((f01 & 0xffffu) | (n01 << 16)) >> off0;
+      if (nterms > 1)
+        fail |= ((f01 >> 16) | (n01 & 0xffff0000u)) >> off1;
+      if (nterms > 2)
+        fail |= (f2 | (n2 << 16)) >> off2;
+      surv = ~fail & 0xffffu;
     }
+    else
+    {
+      exact = true;
+      surv = exact_chunk_candidates(t, P, T, sbase + lane * 16, w[0], w[1], w[2], w[3], w[4], w[5]);
+    }
+    if (!__any_sync(0xffffffffu, surv != 0))
+      return false;
+    // ---- compaction + balanced stage 2
+    uint32_t qn = 0;
+    while (__any_sync(0xffffffffu, surv != 0))
+    {
+      const bool has = surv != 0;
+      const uint32_t b = __ballot_sync(0xffffffffu, has);
+      if (has)
+      {
+        const uint32_t k = __ffs(surv) - 1;
+        surv &= surv - 1;
+        queue[qn + __popc(b & ((1u << lane) - 1))] = static_cast<uint16_t>(lane * 16 + k);
+      }
+      qn += __popc(b);
+      __syncwarp();
+      if (qn >= 32)
+      {
+        qn -= 32;
+        try_at(sbase, queue[qn + lane], exact);
+        __syncwarp();
+      }
+    }
+    if (lane < qn)
+      try_at(sbase, queue[lane], exact);
+    __syncwarp();
+    const uint32_t word = succ[lane >> 1];
+    __syncwarp();
+    if (lane < 16)
+      succ[lane] = 0;
+    __syncwarp();
+    succ16 = (word >> (16 * (lane & 1))) & 0xffffu;
     return __any_sync(0xffffffffu, succ16 != 0);
   }
 };
 
 } // namespace
 
-template <int KIND, bool WANT_NL>
-__global__ void __launch_bounds__(STREAM_THREADS, 2)
+template <int KIND, bool WANT_NL, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 2)
 count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, StreamArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem[];
+  constexpr uint32_t NWARPS = THREADS / 32;
   uint8_t* s_cls = smem;
   uint8_t* s_pred = s_cls + 256;
   uint8_t* s_tap = s_pred + UGX_HASH;
-  uint16_t* s_next = reinterpret_cast<uint16_t*>(s_tap + UGX_BTAP);
+  uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_tap + UGX_BTAP);
+  uint32_t* s_succ = s_lut + 256;
+  uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_succ + 16 * NWARPS);
+  uint32_t* s_h4 = reinterpret_cast<uint32_t*>(s_queue + 64 * NWARPS);
+  uint16_t* s_next = reinterpret_cast<uint16_t*>(s_h4 + (a.use_h4 ? UGX_HASH : 0));
   for (uint32_t i = threadIdx.x; i < 256 / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(s_cls)[i] = __ldg(reinterpret_cast<const uint32_t*>(P.cls) + i);
   for (uint32_t i = threadIdx.x; i < UGX_HASH / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(s_pred)[i] = __ldg(reinterpret_cast<const uint4*>(P.pred) + i);
   for (uint32_t i = threadIdx.x; i < UGX_BTAP / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(s_tap)[i] = __ldg(reinterpret_cast<const uint4*>(P.tap) + i);
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
+    s_lut[i] = P.plan.lut[i];
+  for (uint32_t i = threadIdx.x; i < 16 * NWARPS; i += blockDim.x)
+    s_succ[i] = 0;
+  if (a.use_h4)
+    for (uint32_t i = threadIdx.x; i < UGX_HASH; i += blockDim.x)
+    {
+      // missing terms (h4_terms < 3) never fail
+      const uint32_t e = __ldg(P.pred + i);
+      uint32_t v = 0;
+      for (uint32_t tt = 0; tt < P.plan.h4_terms; ++tt)
+        v |= ((e >> (3 + tt)) & 1u) << (8 * tt);
+      s_h4[i] = v;
+    }
   if (a.stage_table)
     for (uint32_t i = threadIdx.x; i < (P.table_bytes + 15) / 16; i += blockDim.x)
       reinterpret_cast<uint4*>(s_next)[i] = __ldg(reinterpret_cast<const uint4*>(P.next) + i);
@@ -145,13 +318,20 @@ count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* _
   T.pred = s_pred;
   T.tap = s_tap;
   T.next = a.stage_table ? s_next : P.next;
-  DfaEval<KIND> ev{P, T, Text{buf, n}, threadIdx.x & 31};
-  stream_scan<WANT_NL>(buf, n, a, ev);
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  DfaEval<KIND> ev{P, T, Text{buf, n}, lane, (lane + 1) & 31, s_lut, a.use_h4 ? s_h4 : nullptr, P.plan.h4_shift,
+                   s_queue + 64 * wid, s_succ + 16 * wid,
+                   P.plan.nterms, P.plan.t_off[0], P.plan.t_off[1], P.plan.t_off[2],
+                   P.plan.kind == FK_LUT && P.plan.nterms >= 1};
+  stream_scan<WANT_NL, false>(buf, n, a, ev);
 }
 
-static size_t stream_smem_bytes(const DevPattern& P, bool stage)
+static bool stream_use_h4(const DevPattern& P) { return P.plan.h4_terms >= 1; }
+
+static size_t stream_smem_bytes(const DevPattern& P, bool stage, int threads)
 {
-  return 256 + UGX_HASH + UGX_BTAP + (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
+  return 256 + UGX_HASH + UGX_BTAP + 1024 + (threads / 32) * (64 + 128) + (stream_use_h4(P) ? 4 * UGX_HASH : 0) +
+         (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
 }
 
 bool count_lines_stream_eligible(const DevPattern& P)
@@ -161,12 +341,13 @@ bool count_lines_stream_eligible(const DevPattern& P)
 
 uint64_t stream_regions(uint64_t n) { return (n + SC_REGION - 1) / SC_REGION; }
 
-int stream_grid(uint64_t n, int sm_count, int per_sm)
+int stream_grid(uint64_t n, int sm_count, int per_sm, int threads)
 {
   if (per_sm < 1)
     per_sm = 1;
   uint64_t g = static_cast<uint64_t>(sm_count) * per_sm;
-  const uint64_t need = (stream_regions(n) + STREAM_THREADS / 32 - 1) / (STREAM_THREADS / 32);
+  const uint64_t warps = threads / 32;
+  const uint64_t need = (stream_regions(n) + warps - 1) / warps;
   if (g > need)
     g = need;
   if (g == 0)
@@ -176,19 +357,19 @@ int stream_grid(uint64_t n, int sm_count, int per_sm)
   return static_cast<int>(g);
 }
 
-template <int KIND, bool WANT_NL>
+template <int KIND, bool WANT_NL, int THREADS>
 static cudaError_t launch_dfa(const DevPattern& P, const uint8_t* buf, uint64_t n, const StreamArgs& a, size_t smem,
                               int sm_count, cudaStream_t st)
 {
-  auto kern = count_lines_stream_kernel<KIND, WANT_NL>;
+  auto kern = count_lines_stream_kernel<KIND, WANT_NL, THREADS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess)
     return e;
   int per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, STREAM_THREADS, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
   if (e != cudaSuccess)
     return e;
-  kern<<<stream_grid(n, sm_count, per_sm), STREAM_THREADS, smem, st>>>(P, buf, n, a);
+  kern<<<stream_grid(n, sm_count, per_sm, THREADS), THREADS, smem, st>>>(P, buf, n, a);
   return cudaGetLastError();
 }
 
@@ -198,14 +379,20 @@ cudaError_t launch_count_lines_stream(const DevPattern& P, const uint8_t* buf, u
   if (count_lines_literal_eligible(P))
     return launch_count_lines_literal(P, buf, n, a, want_nl, sm_count, st);
   const bool meta = P.has_meta != 0;
-  const bool stage = !meta && stream_smem_bytes(P, true) <= 227 * 1024 - 2048;
-  const size_t smem = stream_smem_bytes(P, stage);
+  const bool stage = !meta && stream_smem_bytes(P, true, 1024) <= 227 * 1024 - 1024;
+  // a big staged table leaves room for one CTA per SM: make it a full 1024-thread CTA
+  const bool big = stage && stream_smem_bytes(P, true, 256) > 100 * 1024;
+  const size_t smem = stream_smem_bytes(P, stage, big ? 1024 : 256);
   a.stage_table = stage ? 1u : 0u;
+  a.use_h4 = stream_use_h4(P) ? 1u : 0u;
   if (meta)
-    return want_nl ? launch_dfa<SK_META, true>(P, buf, n, a, smem, sm_count, st)
-                   : launch_dfa<SK_META, false>(P, buf, n, a, smem, sm_count, st);
-  return want_nl ? launch_dfa<SK_TABLE, true>(P, buf, n, a, smem, sm_count, st)
-                 : launch_dfa<SK_TABLE, false>(P, buf, n, a, smem, sm_count, st);
+    return want_nl ? launch_dfa<SK_META, true, 256>(P, buf, n, a, smem, sm_count, st)
+                   : launch_dfa<SK_META, false, 256>(P, buf, n, a, smem, sm_count, st);
+  if (big)
+    return want_nl ? launch_dfa<SK_TABLE, true, 1024>(P, buf, n, a, smem, sm_count, st)
+                   : launch_dfa<SK_TABLE, false, 1024>(P, buf, n, a, smem, sm_count, st);
+  return want_nl ? launch_dfa<SK_TABLE, true, 256>(P, buf, n, a, smem, sm_count, st)
+                 : launch_dfa<SK_TABLE, false, 256>(P, buf, n, a, smem, sm_count, st);
 }
 
 } // namespace ugx

@@ -100,7 +100,7 @@ count_lines_literal_kernel(const __grid_constant__ DevPattern P, const uint8_t* 
   ev.sh1 = (P.plan.a_off[1] & 3) * 8;
   ev.lane = threadIdx.x & 31;
   asm volatile("" : "+r"(ev.lane));
-  stream_scan<WANT_NL>(buf, n, a, ev);
+  stream_scan<WANT_NL, true>(buf, n, a, ev);
 }
 
 bool count_lines_literal_eligible(const DevPattern& P)
@@ -118,7 +118,7 @@ static cudaError_t launch_literal(const DevPattern& P, const uint8_t* buf, uint6
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, STREAM_THREADS, 0);
   if (e != cudaSuccess)
     return e;
-  kern<<<stream_grid(n, sm_count, per_sm), STREAM_THREADS, 0, st>>>(P, buf, n, a);
+  kern<<<stream_grid(n, sm_count, per_sm, STREAM_THREADS), STREAM_THREADS, 0, st>>>(P, buf, n, a);
   return cudaGetLastError();
 }
 
