@@ -363,7 +363,7 @@ def main():
             "hbm_frac": round(value / world / peak, 4),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": None, "peak_kind": peak_kind,
-                         "kernel": "scan_lines_kernel", "kernel_ms": round(k_ms, 4)},
+                         "kernel": tot.kernel, "kernel_ms": round(k_ms, 4)},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": launches,

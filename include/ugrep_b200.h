@@ -131,9 +131,14 @@ typedef struct ugx_totals {
   uint64_t long_lines;     /* lines that took the long-line path */
   float    kernel_ms;      /* device time of the scan kernels (CUDA events on the scan stream) */
   uint32_t launches;       /* kernels launched by this call */
+  uint32_t kernel;         /* UGX_K_*: the scan kernel that did the work (ugx_kernel_name) */
 } ugx_totals;
 
+/* scan kernels (reported in ugx_totals.kernel) */
+enum { UGX_K_NONE = 0, UGX_K_STREAM_LITERAL = 1, UGX_K_STREAM_DFA = 2, UGX_K_TILE_ANY = 3, UGX_K_LINE_SCAN = 4 };
+
 const char *ugx_last_error(void);
+const char *ugx_kernel_name(uint32_t id);
 int  ugx_abi_version(void);
 
 /* pattern: flatten the opcode table to a dense class-compressed DFA and upload it with the prefilter tables */
@@ -146,7 +151,11 @@ void ugx_pattern_destroy(ugx_pattern *p);
 /* scanner: owns a stream-ordered scratch arena on `device`; `stream` is a cudaStream_t (NULL = default stream) */
 int  ugx_scanner_create(int device, void *stream, ugx_scanner **out);
 void ugx_scanner_destroy(ugx_scanner *s);
-/* options: "force_generic" = 1 makes every scan take the generic line-scan kernel (used by the tests) */
+/* options (tests and A/B timing; defaults 0):
+ *   "force_generic"   every scan takes the generic line-scan kernel
+ *   "legacy_any"      `-c` takes the tile-synchronous kernel instead of the streaming one
+ *   "stream_dfa"      `-c` of every eligible DFA pattern takes the streaming kernel
+ *   "count_newlines"  the streaming `-c` kernels also count newlines (totals.newlines) */
 int  ugx_scanner_set_option(ugx_scanner *s, const char *name, int value);
 
 /*

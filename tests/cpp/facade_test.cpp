@@ -1,6 +1,6 @@
 // tests/cpp/facade_test.cpp — drives the C++ mirror of reflex::Matcher (include/ugrep_b200/matcher.hpp) with the
 // caller loops of Grep::search (/root/reference/src/ugrep.cpp:10536-10586, :10857-11047) and prints what
-// `ugrep -c`, `ugrep -c -o` and `ugrep -n -b -o` print.  Usage: facade_test PATTERN.ugxp MODE FILE   MODE: cl|cm|list|cl_loop
+// `ugrep -c`, `ugrep -c -o` and `ugrep -n -b -o` print.  Usage: facade_test PATTERN.ugxp MODE FILE   MODE: cl|cm|list|cl_loop|all
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -41,6 +41,26 @@ int main(int argc, char** argv)
         matcher.skip_line();
       }
       printf("%zu\n", lines);
+    }
+    else if (mode == "all")
+    {
+      // every loop in one process: counts first, then the -n -b -o listing
+      printf("cl=%zu\n", matcher.count_lines());
+      printf("cm=%zu\n", matcher.count_matches());
+      size_t lines = 0;
+      while (matcher.find())
+      {
+        ++lines;
+        matcher.skip_line();
+      }
+      printf("loop=%zu\n", lines);
+      matcher.reset();
+      while (matcher.find())
+      {
+        printf("%zu:%zu:", matcher.lineno(), matcher.first());
+        fwrite(matcher.begin(), 1, matcher.size(), stdout);
+        fputc('\n', stdout);
+      }
     }
     else if (mode == "list")
     {

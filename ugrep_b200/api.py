@@ -25,7 +25,7 @@ MATCH_DTYPE = np.dtype([("line", "<u8"), ("offset", "<u8"), ("len", "<u4"), ("ca
 ADVANCE_NAMES = ["none", "pin1_one", "pin1_pma", "pin1_pmh", "pin_one", "pin_pma", "pin_pmh", "min1", "min2", "min3",
                  "min4", "pma", "char", "char_pma", "char_pmh", "string", "string_pma", "string_pmh"]
 
-EXPORTS = ["ugx_last_error", "ugx_abi_version", "ugx_pattern_create", "ugx_pattern_load", "ugx_pattern_info_get",
+EXPORTS = ["ugx_last_error", "ugx_kernel_name", "ugx_abi_version", "ugx_pattern_create", "ugx_pattern_load", "ugx_pattern_info_get",
            "ugx_pattern_destroy", "ugx_scanner_create", "ugx_scanner_destroy", "ugx_count_lines", "ugx_count_matches",
            "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_scanner_set_option", "ugx_count_newlines"]
 
@@ -38,7 +38,7 @@ class UgxError(RuntimeError):
 
 class _Totals(C.Structure):
     _fields_ = [("matches", C.c_uint64), ("newlines", C.c_uint64), ("long_lines", C.c_uint64),
-                ("kernel_ms", C.c_float), ("launches", C.c_uint32)]
+                ("kernel_ms", C.c_float), ("launches", C.c_uint32), ("kernel", C.c_uint32)]
 
 
 class _Info(C.Structure):
@@ -53,6 +53,7 @@ class Totals:
     long_lines: int
     kernel_ms: float
     launches: int
+    kernel: str = "none"
 
 
 _lib = None
@@ -67,6 +68,8 @@ def lib():
                            % LIB_PATH)
         L = C.CDLL(LIB_PATH)
         L.ugx_last_error.restype = C.c_char_p
+        L.ugx_kernel_name.restype = C.c_char_p
+        L.ugx_kernel_name.argtypes = [C.c_uint32]
         L.ugx_pattern_create.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
         L.ugx_pattern_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         L.ugx_pattern_info_get.argtypes = [C.c_void_p, C.POINTER(_Info)]
@@ -153,7 +156,8 @@ class Scanner:
         _check(lib().ugx_scanner_set_option(self._h, name.encode(), int(value)))
 
     def _totals(self, t: _Totals) -> Totals:
-        return Totals(t.matches, t.newlines, t.long_lines, t.kernel_ms, t.launches)
+        return Totals(t.matches, t.newlines, t.long_lines, t.kernel_ms, t.launches,
+                      lib().ugx_kernel_name(t.kernel).decode())
 
     def count_lines(self, pattern: Pattern, data) -> Totals:
         ptr, n, keep = _buffer(data)

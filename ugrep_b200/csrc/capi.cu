@@ -441,7 +441,7 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
   a.base_line = base_line;
   CU(cudaEventRecord(s->ev0, s->stream));
   if (mode == 0 && !want_records && !s->force_generic && !s->legacy_any && ugx::count_lines_stream_eligible(p->dev) &&
-      (s->stream_dfa || ugx::count_lines_literal_eligible(p->dev)))
+      (s->stream_dfa || ugx::count_lines_literal_eligible(p->dev) || p->dev.plan.h4_terms >= 1))
   {
     rc = ensure(s->region_sum, s->region_cap, ugx::stream_regions(n) + 64);
     if (rc != UGX_OK)
@@ -459,17 +459,20 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
     sa.use_h4 = 0;
     CU(ugx::launch_count_lines_stream(p->dev, dbuf, n, sa, s->count_newlines, s->sm_count, s->stream));
     tt.launches = 1;
+    tt.kernel = ugx::count_lines_literal_eligible(p->dev) ? UGX_K_STREAM_LITERAL : UGX_K_STREAM_DFA;
   }
   else if (mode == 0 && !want_records && !s->force_generic && ugx::count_lines_any_eligible(p->dev))
   {
     CU(ugx::launch_count_lines_any(p->dev, dbuf, n, s->totals, s->sm_count, s->stream));
     tt.launches = 1;
+    tt.kernel = UGX_K_TILE_ANY;
   }
   else
   {
     CU(ugx::launch_scan_lines(p->dev, a, mode, false, s->sm_count, s->stream));
     CU(ugx::launch_tile_prefix(s->tile_matches, s->tile_newlines, ntiles, s->totals, s->stream));
     tt.launches = 2;
+    tt.kernel = UGX_K_LINE_SCAN;
   }
   CU(cudaMemcpyAsync(s->h_totals, s->totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
   if (want_records)
@@ -544,6 +547,18 @@ int ugx_find_all(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t
     CU(cudaStreamSynchronize(s->stream));
   }
   return UGX_OK;
+}
+
+const char* ugx_kernel_name(uint32_t id)
+{
+  switch (id)
+  {
+    case UGX_K_STREAM_LITERAL: return "count_lines_literal_kernel";
+    case UGX_K_STREAM_DFA: return "count_lines_stream_kernel";
+    case UGX_K_TILE_ANY: return "count_lines_any_kernel";
+    case UGX_K_LINE_SCAN: return "scan_lines_kernel";
+    default: return "none";
+  }
 }
 
 int ugx_scanner_set_option(ugx_scanner* s, const char* name, int value)

@@ -14,7 +14,7 @@ constexpr int SCAN_THREADS = 256;                      // threads per CTA
 constexpr int SCAN_STRIP = 64;                         // bytes per thread per tile
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_STRIP;   // bytes per CTA iteration (16 KiB)
 constexpr uint32_t SCAN_LINE_CAP = 1024;                // line starts per tile the dense line list holds
-constexpr uint32_t SCAN_MAX_SMEM_TABLE = 200 * 1024;   // largest transition table staged in shared memory
+constexpr uint32_t SCAN_MAX_SMEM_TABLE = 198 * 1024;   // largest transition table staged in shared memory
 constexpr uint32_t ANY_TILE = 32768;                   // bytes per CTA iteration of count_lines_any_kernel
 
 struct ScanArgs {
