@@ -208,3 +208,34 @@ def test_stream_count_ragged_and_chained(gpu):
                 t = sc2.count_lines(pat, data)
                 assert t.matches == want and t.newlines == int((data == 10).sum()), (pname, n, "nl")
     sc.set_option("stream_dfa", 0)
+
+
+def test_pipelined_host_buffer_equals_device_scan(gpu):
+    """host buffers >= 64 MiB on the streaming route are copied in chunks while earlier chunks are scanned; the
+    region summaries chain the launches.  Counts must equal the one-launch device-resident scan and the oracle
+    (additive over line-aligned repetitions of one block)."""
+    import torch
+    api, sc = gpu
+    for pname, cname in (("c1", "c1"), ("c2", "c2")):
+        path = os.path.join(PAT_DIR, pname + ".ugxp")
+        pat = api.Pattern.load(path, 0)
+        op = O.OraclePattern(path)
+        block = corpus.block(cname, 5 << 20)
+        assert block[-1] == 10
+        reps = 15  # 75 MiB: three chunks of the pipeline, the last one partial
+        # a line that straddles every block boundary would break additivity: blocks end with a newline
+        host = np.tile(block, reps)
+        # put a literal across a 32 MiB chunk boundary (c1) so that the lag of one region is exercised
+        if pname == "c1":
+            at = (32 << 20) - 7
+            host = host.copy()
+            host[at:at + 15] = np.frombuffer(b"Sherlock Holmes", dtype=np.uint8)
+        want_dev = sc.count_lines(pat, torch.from_numpy(host).cuda())
+        got = sc.count_lines(pat, host)
+        assert got.launches >= 3, got
+        assert got.matches == want_dev.matches
+        sc.set_option("no_pipeline", 1)
+        assert sc.count_lines(pat, host).matches == want_dev.matches
+        sc.set_option("no_pipeline", 0)
+        if pname == "c2":
+            assert got.matches == reps * op.count_lines(block)

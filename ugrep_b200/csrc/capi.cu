@@ -108,6 +108,9 @@ struct ugx_scanner {
   bool force_generic = false; // tests: always take the generic line-scan kernel
   bool legacy_any = false;    // tests / A-B timing: the tile-synchronous count_lines_any kernel instead of the streaming one
   bool count_newlines = false; // the streaming count also counts newlines
+  bool no_pipeline = false;    // host buffers: one copy, then the scan (A/B timing of the overlapped path)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr;
   bool stream_dfa = false;     // DFA patterns take the streaming count too (default: the tile-synchronous kernel)
   // streaming count scratch
   uint8_t* region_sum = nullptr;
@@ -293,6 +296,10 @@ int ugx_scanner_create(int device, void* stream, ugx_scanner** out)
   if (e == cudaSuccess)
     e = cudaEventCreate(&s->ev1);
   if (e == cudaSuccess)
+    e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess)
+    e = cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming);
+  if (e == cudaSuccess)
     e = cudaMalloc(reinterpret_cast<void**>(&s->totals), 4 * sizeof(unsigned long long));
   if (e == cudaSuccess)
     e = cudaMallocHost(reinterpret_cast<void**>(&s->h_totals), 4 * sizeof(unsigned long long));
@@ -331,6 +338,10 @@ void ugx_scanner_destroy(ugx_scanner* s)
     cudaEventDestroy(s->ev0);
   if (s->ev1)
     cudaEventDestroy(s->ev1);
+  if (s->ev_copy)
+    cudaEventDestroy(s->ev_copy);
+  if (s->copy_stream)
+    cudaStreamDestroy(s->copy_stream);
   delete s;
 }
 
@@ -392,6 +403,20 @@ int resolve(ugx_scanner* s, const void* buf, uint64_t n, const uint8_t** dev, ui
   return UGX_OK;
 }
 
+constexpr uint64_t PIPE_CHUNK = 32ull << 20; // bytes per host-to-device chunk of the pipelined path (region-aligned)
+
+bool is_host_pointer(const void* buf)
+{
+  cudaPointerAttributes at;
+  const cudaError_t e = cudaPointerGetAttributes(&at, buf);
+  if (e != cudaSuccess)
+  {
+    cudaGetLastError();
+    return true;
+  }
+  return at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged;
+}
+
 int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t n, int mode, bool want_records,
                 uint64_t base_offset, uint64_t base_line, const ugx_match** dev_out, uint64_t* n_out, ugx_totals* totals)
 {
@@ -414,7 +439,22 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
   CU(cudaSetDevice(s->device));
   const uint8_t* dbuf = nullptr;
   uint64_t h2d = 0;
-  int rc = resolve(s, buf, n, &dbuf, &h2d);
+  const bool stream_route = mode == 0 && !want_records && !s->force_generic && !s->legacy_any &&
+                            ugx::count_lines_stream_eligible(p->dev) &&
+                            (s->stream_dfa || ugx::count_lines_literal_eligible(p->dev) || p->dev.plan.h4_terms >= 1);
+  // a host buffer on the streaming route is copied chunk by chunk, overlapped with the scan, when every read of a
+  // scanned position stays within one region of it: pure literals, and DFAs whose longest match is bounded
+  const bool bounded = ugx::count_lines_literal_eligible(p->dev) || p->dfa.max_match_len < ugx::SC_REGION - 512;
+  const bool pipelined = stream_route && bounded && !s->no_pipeline && n >= 2 * PIPE_CHUNK && is_host_pointer(buf);
+  int rc;
+  if (pipelined)
+  {
+    rc = ensure(s->stage, s->stage_cap, n + 16);
+    dbuf = s->stage;
+    h2d = n;
+  }
+  else
+    rc = resolve(s, buf, n, &dbuf, &h2d);
   if (rc != UGX_OK)
     return rc;
   const uint64_t ntiles = (n + ugx::SCAN_TILE - 1) / ugx::SCAN_TILE;
@@ -440,25 +480,59 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
   a.base_offset = base_offset;
   a.base_line = base_line;
   CU(cudaEventRecord(s->ev0, s->stream));
-  if (mode == 0 && !want_records && !s->force_generic && !s->legacy_any && ugx::count_lines_stream_eligible(p->dev) &&
-      (s->stream_dfa || ugx::count_lines_literal_eligible(p->dev) || p->dev.plan.h4_terms >= 1))
+  if (stream_route)
   {
     rc = ensure(s->region_sum, s->region_cap, ugx::stream_regions(n) + 64);
     if (rc != UGX_OK)
       return rc;
     ugx::StreamArgs sa;
     sa.region_sum = s->region_sum;
-    sa.first_region = 0;
     sa.partials = s->partials;
     sa.ticket = s->ticket;
     sa.done = reinterpret_cast<unsigned int*>(s->ticket + 1);
     sa.totals = s->totals;
-    sa.finalize = 1;
-    sa.accumulate = 0;
     sa.stage_table = 0;
     sa.use_h4 = 0;
-    CU(ugx::launch_count_lines_stream(p->dev, dbuf, n, sa, s->count_newlines, s->sm_count, s->stream));
-    tt.launches = 1;
+    const uint64_t nreg = ugx::stream_regions(n);
+    if (pipelined)
+    {
+      // host buffer: copy in chunks on the copy stream and scan chunk i while chunk i + 1 is in flight.  A launch
+      // trails the copied bytes by one region, so that every read of a scanned position (literal verify, a DFA
+      // attempt of bounded length) finds its bytes; the region summaries chain the launches.
+      uint64_t copied = 0, scanned = 0;
+      tt.launches = 0;
+      while (scanned < nreg)
+      {
+        const uint64_t take = n - copied < PIPE_CHUNK ? n - copied : PIPE_CHUNK;
+        if (take > 0)
+        {
+          CU(cudaMemcpyAsync(s->stage + copied, static_cast<const uint8_t*>(buf) + copied, take, cudaMemcpyHostToDevice,
+                             s->copy_stream));
+          copied += take;
+          CU(cudaEventRecord(s->ev_copy, s->copy_stream));
+          CU(cudaStreamWaitEvent(s->stream, s->ev_copy, 0));
+        }
+        const uint64_t upto = copied == n ? nreg : copied / ugx::SC_REGION - 1;
+        if (upto <= scanned)
+          continue;
+        sa.region_begin = scanned;
+        sa.region_end = upto;
+        sa.finalize = upto == nreg ? 1u : 0u;
+        sa.accumulate = scanned == 0 ? 0u : 1u;
+        CU(ugx::launch_count_lines_stream(p->dev, dbuf, copied, sa, s->count_newlines, s->sm_count, s->stream));
+        scanned = upto;
+        ++tt.launches;
+      }
+    }
+    else
+    {
+      sa.region_begin = 0;
+      sa.region_end = nreg;
+      sa.finalize = 1;
+      sa.accumulate = 0;
+      CU(ugx::launch_count_lines_stream(p->dev, dbuf, n, sa, s->count_newlines, s->sm_count, s->stream));
+      tt.launches = 1;
+    }
     tt.kernel = ugx::count_lines_literal_eligible(p->dev) ? UGX_K_STREAM_LITERAL : UGX_K_STREAM_DFA;
   }
   else if (mode == 0 && !want_records && !s->force_generic && ugx::count_lines_any_eligible(p->dev))
@@ -573,6 +647,11 @@ int ugx_scanner_set_option(ugx_scanner* s, const char* name, int value)
   if (strcmp(name, "legacy_any") == 0)
   {
     s->legacy_any = value != 0;
+    return UGX_OK;
+  }
+  if (strcmp(name, "no_pipeline") == 0)
+  {
+    s->no_pipeline = value != 0;
     return UGX_OK;
   }
   if (strcmp(name, "stream_dfa") == 0)

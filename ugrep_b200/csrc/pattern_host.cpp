@@ -267,6 +267,77 @@ int flatten_dfa(const uint32_t* opc, uint32_t nop, HostDfa& out, std::string& er
     }
   }
   out.meta_off[ns] = static_cast<uint32_t>(out.metas.size());
+  // longest match: longest path from the start state (byte edges weigh 1, META edges 0); a cycle makes it unbounded
+  {
+    std::vector<int> color(ns, 0);          // 0 new, 1 on the stack, 2 done
+    std::vector<uint32_t> depth(ns, 0);     // longest path from the state
+    std::vector<std::pair<uint32_t, uint32_t>> stack; // (state, next successor index)
+    bool cyclic = false;
+    auto succ = [&](uint32_t s, uint32_t i, uint32_t& to, uint32_t& w) -> bool {
+      if (i < ncls)
+      {
+        const uint16_t t = out.next[static_cast<size_t>(s) * ncls + i];
+        to = t;
+        w = 1;
+        return true;
+      }
+      const uint32_t m = out.meta_off[s] + (i - ncls);
+      if (m < out.meta_off[s + 1])
+      {
+        to = out.metas[m].target;
+        w = 0;
+        return true;
+      }
+      return false;
+    };
+    stack.emplace_back(0u, 0u);
+    color[0] = 1;
+    while (!stack.empty() && !cyclic)
+    {
+      const uint32_t s = stack.back().first;
+      uint32_t to = 0, w = 0;
+      if (!succ(s, stack.back().second, to, w))
+      {
+        color[s] = 2;
+        stack.pop_back();
+        continue;
+      }
+      ++stack.back().second;
+      if (to == DEAD)
+        continue;
+      if (color[to] == 1)
+        cyclic = true;
+      else if (color[to] == 0)
+      {
+        color[to] = 1;
+        stack.emplace_back(to, 0u);
+      }
+    }
+    if (cyclic)
+      out.max_match_len = 0xFFFFFFFFu;
+    else
+    {
+      // states in reverse finishing order are not kept: relax repeatedly (ns is small, the graph acyclic)
+      bool changed = true;
+      while (changed)
+      {
+        changed = false;
+        for (uint32_t s = 0; s < ns; ++s)
+          for (uint32_t i = 0;; ++i)
+          {
+            uint32_t to = 0, w = 0;
+            if (!succ(s, i, to, w))
+              break;
+            if (to != DEAD && depth[to] + w > depth[s])
+            {
+              depth[s] = depth[to] + w;
+              changed = true;
+            }
+          }
+      }
+      out.max_match_len = depth[0];
+    }
+  }
   return UGX_OK;
 }
 

@@ -41,6 +41,7 @@ struct HostDfa {
   // byte edges, then states without byte edges ("leaves": the interpreter halts there before reading)
   uint32_t first_acc = 0;          // ids >= first_acc (other than 0) are accepting or leaves
   uint32_t first_leaf = 0;         // ids >= first_leaf (other than 0) are leaves
+  uint32_t max_match_len = 0;      // longest match in bytes; UINT32_MAX when the DFA has a cycle (unbounded)
   uint32_t table_bytes() const { return nstates * ncls * 2; }
 };
 

@@ -47,8 +47,9 @@ constexpr uint32_t SC_REGION = UGX_SC_REGION;                  // bytes per regi
 constexpr uint32_t STREAM_MAX_GRID = 4096;             // capacity of the per-CTA partials
 
 struct StreamArgs {
-  uint8_t* region_sum;            // [first_region + regions(n) + 16] one summary byte per region
-  uint64_t first_region;          // index of this launch's first region within the whole buffer
+  uint8_t* region_sum;            // [regions(buffer) + 16] one summary byte per region of the buffer
+  uint64_t region_begin;          // this launch scans the regions [region_begin, region_end) of the buffer;
+  uint64_t region_end;            //   the kernel's n = the bytes of the buffer that are valid (copied) so far
   unsigned long long* partials;   // [2 * STREAM_MAX_GRID] per-CTA {lines, newlines}
   unsigned long long* ticket;     // region ticket counter (zero between launches)
   unsigned int* done;             // finished-CTA counter (zero between launches)

@@ -182,7 +182,7 @@ __device__ __forceinline__ void stream_epilogue(const StreamArgs& a, uint64_t nr
   if (a.finalize)
   {
     // thread i chains the slice [lo, hi) assuming no carry in; the slices are then chained serially
-    const uint64_t total = a.first_region + nregions;
+    const uint64_t total = nregions;
     const uint64_t per = ((total + blockDim.x - 1) / blockDim.x + 15) & ~15ull;
     const uint64_t lo = threadIdx.x * per;
     const uint64_t hi = lo + per < total ? lo + per : total;
@@ -388,12 +388,14 @@ __device__ __forceinline__ void stream_scan(const uint8_t* __restrict__ buf, uin
   uint32_t lane = threadIdx.x & 31;
   uint32_t next_lane = (lane + 1) & 31;
   asm volatile("" : "+r"(lane), "+r"(next_lane)); // opaque: no re-reading of %tid in the hot loop
-  const uint64_t nregions = (n + SC_REGION - 1) / SC_REGION;
+  // this launch scans the regions [region_begin, region_end) of the buffer; n = bytes of the buffer that are valid
+  // (a host buffer is scanned while it is still being copied: capi.cu)
+  const uint64_t nregions = a.region_end;
   unsigned long long my_lines = 0, my_newlines = 0;
   uint32_t warp_uniform_lines = 0;
   RegionSchedule sched;
-  sched.init(a.ticket, nregions);
-  uint64_t r = sched.next(lane);
+  sched.init(a.ticket, a.region_end - a.region_begin);
+  uint64_t r = a.region_begin + sched.next(lane);
   uint4 v[SC_SPANS];
   uint4 h = make_uint4(0, 0, 0, 0);
   if (r < nregions)
@@ -407,7 +409,7 @@ __device__ __forceinline__ void stream_scan(const uint8_t* __restrict__ buf, uin
   while (r < nregions)
   {
     const uint64_t rbase = r * SC_REGION;
-    const uint64_t rnext = sched.next(lane);
+    const uint64_t rnext = a.region_begin + sched.next(lane);
     const bool have_next = rnext < nregions;
     const uint64_t next_rbase = rnext * SC_REGION;
     LineState L;
@@ -426,7 +428,7 @@ __device__ __forceinline__ void stream_scan(const uint8_t* __restrict__ buf, uin
     if (lane == 0)
     {
       const uint32_t g = L.seen_nl ? L.cin : (L.head ? 1u : 0u);
-      a.region_sum[a.first_region + r] = static_cast<uint8_t>((L.seen_nl ? 1u : 0u) | (L.head ? 2u : 0u) | (g << 2));
+      a.region_sum[r] = static_cast<uint8_t>((L.seen_nl ? 1u : 0u) | (L.head ? 2u : 0u) | (g << 2));
     }
     my_lines += L.lcount;
     warp_uniform_lines += L.ucount;

@@ -369,7 +369,7 @@ static cudaError_t launch_dfa(const DevPattern& P, const uint8_t* buf, uint64_t 
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
   if (e != cudaSuccess)
     return e;
-  kern<<<stream_grid(n, sm_count, per_sm, THREADS), THREADS, smem, st>>>(P, buf, n, a);
+  kern<<<stream_grid((a.region_end - a.region_begin) * SC_REGION, sm_count, per_sm, THREADS), THREADS, smem, st>>>(P, buf, n, a);
   return cudaGetLastError();
 }
 

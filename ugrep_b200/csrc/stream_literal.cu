@@ -118,7 +118,7 @@ static cudaError_t launch_literal(const DevPattern& P, const uint8_t* buf, uint6
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, STREAM_THREADS, 0);
   if (e != cudaSuccess)
     return e;
-  kern<<<stream_grid(n, sm_count, per_sm, STREAM_THREADS), STREAM_THREADS, 0, st>>>(P, buf, n, a);
+  kern<<<stream_grid((a.region_end - a.region_begin) * SC_REGION, sm_count, per_sm, STREAM_THREADS), STREAM_THREADS, 0, st>>>(P, buf, n, a);
   return cudaGetLastError();
 }
 
