@@ -93,6 +93,19 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def measured_traffic(cfg: str, kernel: str, nbytes: int):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json);
+    None unless the capture was taken on this workload size and kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(cfg)
+        if t and t["kernel"] == kernel and t["nbytes"] == nbytes:
+            return int(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def make_block(cfg: str):
     from ugrep_b200 import corpus
     return corpus.block(CONFIGS[cfg][1], BLOCK_BYTES)
@@ -362,7 +375,8 @@ def main():
                        "table_in_smem": bool(info["table_in_smem"])},
             "hbm_frac": round(value / world / peak, 4),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_kind": peak_kind,
+                         "frac": round(achieved / peak, 4), "traffic": measured_traffic(cfg, tot.kernel, nbytes),
+                         "algorithmic_bytes": nbytes, "peak_kind": peak_kind,
                          "kernel": tot.kernel, "kernel_ms": round(k_ms, 4)},
             "cpu_baseline": cpu,
             "e2e": e2e,
