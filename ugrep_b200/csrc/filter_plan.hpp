@@ -32,6 +32,10 @@ struct FilterPlan {
                                     //   bit (3 + t) of pmh[g(k + h4_shift + 3 + t)] is clear, g = the 12-bit rolling hash of
                                     //   the 4 bytes ending at its argument (Pattern::predict_match steps 3, 4, 5)
   uint32_t h4_shift;                // the predictor starts at k + h4_shift (1 for the CHAR_PMH routine, else 0)
+  uint32_t pm2;                     // 1: PM4 two-byte term (min_ < 4): with q7 q6 = bits 7, 6 of pma[c0] and q5 q4 = bits 5, 4
+                                    //   of pma[hash(c0, c1)], position k fails iff q7 & q5 & (q4 | q6) — the part of
+                                    //   Pattern::predict_match's PM4 formula that the first two bytes decide
+  uint32_t pm2_shift;               // the predictor starts at k + pm2_shift (1 for the CHAR_PMA routine, else 0)
   uint32_t est_pass_ppm;            // planner's estimate of the survivor rate (informational)
   uint32_t lut[256];                // FK_LUT: bit 8*t of lut[c] set = byte c FAILS term t (the planes are byte-
                                     // aligned so that eight positions accumulate in one register: acc = 2*acc + lut[c])

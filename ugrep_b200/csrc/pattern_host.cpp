@@ -421,6 +421,13 @@ void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan)
     plan.h4_terms = pf.min - 3 > 3 ? 3 : pf.min - 3;
     plan.h4_shift = adv == UGX_ADV_CHAR_PMH ? 1 : 0;
   }
+  // PM4 two-byte term for the routines that call predict_match PM4 on every interior candidate and have no
+  // selective byte-set term of their own
+  if (pf.min < 4 && (adv == UGX_ADV_PMA || adv == UGX_ADV_MIN1 || adv == UGX_ADV_MIN2 || adv == UGX_ADV_MIN3))
+  {
+    plan.pm2 = 1;
+    plan.pm2_shift = 0;
+  }
   switch (adv)
   {
     case UGX_ADV_STRING:

@@ -269,8 +269,6 @@ __device__ __forceinline__ void stream_epilogue(const StreamArgs& a, uint64_t nr
 // Eval: bool operator()(const uint32_t (&w)[7], uint64_t sbase, uint32_t& succ16) — evaluates one span (w = the
 // lane's 16 bytes + 12 halo bytes), sets the lane's 16-bit success mask and returns the
 // warp-uniform "some lane has a success".
-constexpr int SC_SPANS = 4;
-constexpr uint32_t SC_BLOCK = SC_SPANS * SC_SPAN;
 
 // one span.  WATCH: a newline would change the line state (cin is set, or the region's first newline is still
 // to come), or newlines are being counted; otherwise the span is only tested for successes.
@@ -310,11 +308,14 @@ __device__ __forceinline__ void stream_span(const uint32_t (&w)[7], uint64_t sba
 
 // one region.  FULL: the region, its halo and the first block of the warp's next region lie wholly inside the
 // buffer, so no load is guarded and no span is tested against the end of the buffer.
-template <bool FULL, bool WANT_NL, bool SPLIT_WATCH, class Eval>
+// SC_SPANS = spans per block (4 for the memory-bound literal kernel; 1 for the DFA kernels, whose span evaluation
+// is large and must not be replicated four times in the instruction stream).
+template <bool FULL, bool WANT_NL, bool SPLIT_WATCH, int SC_SPANS, class Eval>
 __device__ __forceinline__ void stream_region(const uint8_t* __restrict__ buf, uint64_t n, uint64_t rbase, bool have_next,
                                               uint64_t next_rbase, uint32_t lane, uint32_t next_lane, uint4 (&v)[SC_SPANS],
                                               uint4& h, LineState& L, unsigned long long& my_newlines, Eval& ev)
 {
+  constexpr uint32_t SC_BLOCK = SC_SPANS * SC_SPAN;
   const uint64_t rend = FULL ? rbase + SC_REGION : (rbase + SC_REGION < n ? rbase + SC_REGION : n);
   const uint32_t nblocks = FULL ? SC_REGION / SC_BLOCK : static_cast<uint32_t>((rend - rbase + SC_BLOCK - 1) / SC_BLOCK);
   const uint8_t* __restrict__ p = buf + rbase + lane * 16; // this lane's chunk 0 of the current block
@@ -382,9 +383,10 @@ __device__ __forceinline__ void stream_region(const uint8_t* __restrict__ buf, u
   }
 }
 
-template <bool WANT_NL, bool SPLIT_WATCH, class Eval>
+template <bool WANT_NL, bool SPLIT_WATCH, int SC_SPANS, class Eval>
 __device__ __forceinline__ void stream_scan(const uint8_t* __restrict__ buf, uint64_t n, const StreamArgs& a, Eval& ev)
 {
+  constexpr uint32_t SC_BLOCK = SC_SPANS * SC_SPAN;
   uint32_t lane = threadIdx.x & 31;
   uint32_t next_lane = (lane + 1) & 31;
   asm volatile("" : "+r"(lane), "+r"(next_lane)); // opaque: no re-reading of %tid in the hot loop
@@ -421,9 +423,9 @@ __device__ __forceinline__ void stream_scan(const uint8_t* __restrict__ buf, uin
     L.lcount = 0;
     const bool full = rbase + SC_REGION + 16 <= n && (!have_next || next_rbase + SC_BLOCK + 16 <= n);
     if (full)
-      stream_region<true, WANT_NL, SPLIT_WATCH>(buf, n, rbase, have_next, next_rbase, lane, next_lane, v, h, L, my_newlines, ev);
+      stream_region<true, WANT_NL, SPLIT_WATCH, SC_SPANS>(buf, n, rbase, have_next, next_rbase, lane, next_lane, v, h, L, my_newlines, ev);
     else
-      stream_region<false, WANT_NL, SPLIT_WATCH>(buf, n, rbase, have_next, next_rbase, lane, next_lane, v, h, L, my_newlines, ev);
+      stream_region<false, WANT_NL, SPLIT_WATCH, SC_SPANS>(buf, n, rbase, have_next, next_rbase, lane, next_lane, v, h, L, my_newlines, ev);
     // publish the region: bit 0 has newline, bit 1 head success, bit 2 carry out
     if (lane == 0)
     {

@@ -105,13 +105,27 @@ __device__ __forceinline__ bool cand_pin_pmh_interior(const Text& t, const DevPa
   return pmh_xy(T.pred, x, y, P.min);
 }
 
+// advance_pattern_pma on an interior position (pos + 7 <= end): predict_match PM4 on the 4 bytes at pos
+__device__ __forceinline__ bool cand_pma_interior(const Text& t, const Tables& T, uint64_t pos)
+{
+  const uint8_t* p = t.b + pos;
+  const uint32_t sh = (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p)) & 3u) * 8;
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(p - (sh >> 3));
+  return pm4_x(T.pred, __funnelshift_r(__ldg(a), __ldg(a + 1), sh));
+}
+
 template <int KIND>
 __device__ __noinline__ bool stage2(Text t, const DevPattern& P, Tables T, uint64_t pos, bool exact)
 {
   if (!exact)
   {
     const bool pin_pmh = P.adv == UGX_ADV_PIN_PMH || P.adv == UGX_ADV_PIN1_PMH;
-    if (pin_pmh && pos + 12 <= t.end ? !cand_pin_pmh_interior(t, P, T, pos) : !cand(t, P, T, pos))
+    if (pos + 12 <= t.end && (pin_pmh || P.adv == UGX_ADV_PMA))
+    {
+      if (pin_pmh ? !cand_pin_pmh_interior(t, P, T, pos) : !cand_pma_interior(t, T, pos))
+        return false;
+    }
+    else if (!cand(t, P, T, pos))
       return false;
   }
   return attempt_at<KIND>(t, P, T, pos);
@@ -152,7 +166,9 @@ struct DfaEval {
   uint32_t lane, next_lane;
   const uint32_t* lut;  // [256] shared: bit 8*t set = the byte fails term t
   const uint32_t* h4;   // [4096] shared: bit 8*t set = pmh[g] fails hashed-predictor step 3 + t; nullptr = unused
+  const uint32_t* h4x;  // [4096] shared: the same storage when it holds the PM4 pair planes
   uint32_t h4_shift;
+  bool pm2;             // lut/h4 hold the PM4 two-byte planes instead (q7 q6 by byte, q5 q4 by pair hash)
   uint16_t* queue;      // [64] per warp
   uint32_t* succ;       // [16] per warp: success bits of the span, bit (16 * lane + k)
   uint32_t nterms, off0, off1, off2;
@@ -169,7 +185,7 @@ struct DfaEval {
     const bool interior = sbase + SC_SPAN + 24 <= t.end; // uniform
     uint32_t surv = 0;
     bool exact;
-    if (h4 != nullptr && interior)
+    if (h4 != nullptr && !pm2 && interior)
     {
       // hashed-predictor terms: one rolling 12-bit hash and one lookup per text byte.  Byte i of the predictor
       // window of position k is text byte k + h4_shift + i; c[] is the chunk shifted by h4_shift.
@@ -203,6 +219,23 @@ struct DfaEval {
       fail |= (((ra >> 16) & 0xffu) >> 1) | (((rb >> 16) & 0xffu) << 7) | (((rc >> 16) & 1u) << 15); // t = 1: k = p - 4
       fail |= (((ra >> 8) & 0xffu) >> 2) | (((rb >> 8) & 0xffu) << 6) | (((rc >> 8) & 3u) << 14);    // t = 2: k = p - 5
       surv = ~fail & 0xffffu;
+    }
+    else if (pm2 && interior)
+    {
+      // PM4 two-byte term: per position one lookup by byte (q7, q6) and one by the pair hash (q5, q4)
+      exact = false;
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int k = 7; k >= 0; --k)
+      {
+        const uint32_t b0 = (w[k >> 2] >> (8 * (k & 3))) & 0xffu, b1 = (w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu;
+        const uint32_t d0 = (w[(k + 8) >> 2] >> (8 * (k & 3))) & 0xffu, d1 = (w[(k + 9) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu;
+        lo = lo * 2 + (lut[b0] | h4x[(b0 << 3) ^ b1]);
+        hi = hi * 2 + (lut[d0] | h4x[(d0 << 3) ^ d1]);
+      }
+      const uint32_t q7 = __byte_perm(lo, hi, 0x4440), q6 = __byte_perm(lo, hi, 0x4451);
+      const uint32_t q5 = __byte_perm(lo, hi, 0x4462), q4 = __byte_perm(lo, hi, 0x4473);
+      surv = ~(q7 & q5 & (q4 | q6)) & 0xffffu;
     }
     else if (use_lut && interior)
     {
@@ -296,7 +329,7 @@ count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* _
   for (uint32_t i = threadIdx.x; i < UGX_BTAP / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(s_tap)[i] = __ldg(reinterpret_cast<const uint4*>(P.tap) + i);
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
-    s_lut[i] = P.plan.lut[i];
+    s_lut[i] = P.plan.pm2 ? (((__ldg(P.pred + i) >> 7) & 1u) | (((__ldg(P.pred + i) >> 6) & 1u) << 8)) : P.plan.lut[i];
   for (uint32_t i = threadIdx.x; i < 16 * NWARPS; i += blockDim.x)
     s_succ[i] = 0;
   if (a.use_h4)
@@ -305,8 +338,11 @@ count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* _
       // missing terms (h4_terms < 3) never fail
       const uint32_t e = __ldg(P.pred + i);
       uint32_t v = 0;
-      for (uint32_t tt = 0; tt < P.plan.h4_terms; ++tt)
-        v |= ((e >> (3 + tt)) & 1u) << (8 * tt);
+      if (P.plan.pm2)
+        v = (((e >> 5) & 1u) << 16) | (((e >> 4) & 1u) << 24);
+      else
+        for (uint32_t tt = 0; tt < P.plan.h4_terms; ++tt)
+          v |= ((e >> (3 + tt)) & 1u) << (8 * tt);
       s_h4[i] = v;
     }
   if (a.stage_table)
@@ -319,14 +355,15 @@ count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* _
   T.tap = s_tap;
   T.next = a.stage_table ? s_next : P.next;
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  DfaEval<KIND> ev{P, T, Text{buf, n}, lane, (lane + 1) & 31, s_lut, a.use_h4 ? s_h4 : nullptr, P.plan.h4_shift,
+  DfaEval<KIND> ev{P, T, Text{buf, n}, lane, (lane + 1) & 31, s_lut, a.use_h4 ? s_h4 : nullptr, s_h4, P.plan.h4_shift,
+                   P.plan.pm2 != 0 && a.use_h4 != 0,
                    s_queue + 64 * wid, s_succ + 16 * wid,
                    P.plan.nterms, P.plan.t_off[0], P.plan.t_off[1], P.plan.t_off[2],
                    P.plan.kind == FK_LUT && P.plan.nterms >= 1};
-  stream_scan<WANT_NL, false>(buf, n, a, ev);
+  stream_scan<WANT_NL, false, 1>(buf, n, a, ev);
 }
 
-static bool stream_use_h4(const DevPattern& P) { return P.plan.h4_terms >= 1; }
+static bool stream_use_h4(const DevPattern& P) { return P.plan.h4_terms >= 1 || P.plan.pm2 != 0; }
 
 static size_t stream_smem_bytes(const DevPattern& P, bool stage, int threads)
 {

@@ -100,7 +100,7 @@ count_lines_literal_kernel(const __grid_constant__ DevPattern P, const uint8_t* 
   ev.sh1 = (P.plan.a_off[1] & 3) * 8;
   ev.lane = threadIdx.x & 31;
   asm volatile("" : "+r"(ev.lane));
-  stream_scan<WANT_NL, true>(buf, n, a, ev);
+  stream_scan<WANT_NL, true, 4>(buf, n, a, ev);
 }
 
 bool count_lines_literal_eligible(const DevPattern& P)
