@@ -120,6 +120,33 @@ def test_ragged_sizes(gpu):
         data = base[:n]
         assert sc.count_matches(pat, data).matches == op.count_matches(data), n
         assert sc.count_lines(pat, data).matches == op.count_lines(data), n
+        if n % 7 == 0 or n > 1000:
+            rec, _ = sc.find_all(pat, data, base_offset=1000, base_line=50)
+            want = op.find_all(data)
+            assert len(rec) == len(want), n
+            assert bool(np.all(rec["offset"] == want["offset"] + 1000)) and bool(np.all(rec["line"] == want["line"] + 50)), n
+            assert bool(np.all(rec["len"] == want["len"])) and bool(np.all(rec["cap"] == want["cap"])), n
+
+
+def test_records_dense_strips_and_long_lines(gpu):
+    """single-pass records: strips with more matches than the shared-memory slots hold (re-run path), lines far
+    longer than a tile, and a first call whose staging guess is too small (second staging pass)"""
+    api, _ = gpu
+    sc = api.Scanner(0)
+    path = os.path.join(PAT_DIR, "c5.ugxp")
+    pat = api.Pattern.load(path, 0)
+    op = O.OraclePattern(path)
+    dense = (b"ERROR WARN 555-1234 WARN ERROR 123-4567 " * 40 + b"\n") * 30          # ~10 matches per 64 bytes
+    long_line = b"x" * 50000 + b" ERROR " + b"y" * 40000 + b" 555-0000 WARN\n" + b"WARN\n" * 5
+    huge = dense * 40                                                               # > n / 96 records: staging regrows
+    for data in (dense, long_line, long_line + dense + long_line, huge):
+        rec, tot = sc.find_all(pat, data)
+        want = op.find_all(data)
+        assert len(rec) == len(want) == tot.matches
+        assert bool(np.all(rec == want))
+    sc.set_option("two_pass_records", 1)
+    rec2, _ = sc.find_all(pat, huge)
+    assert bool(np.all(rec2 == op.find_all(huge)))
 
 
 @pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref (the built reference) did not travel")
@@ -147,7 +174,8 @@ def test_config_vs_reference_cli(gpu, name, cli):
 import golden_lib as G  # noqa: E402
 
 ROUTES = {"default": {}, "generic": {"force_generic": 1}, "legacy_any": {"legacy_any": 1},
-          "stream": {"stream_dfa": 1}, "stream_nl": {"stream_dfa": 1, "count_newlines": 1}}
+          "stream": {"stream_dfa": 1}, "stream_nl": {"stream_dfa": 1, "count_newlines": 1},
+          "two_pass": {"two_pass_records": 1}}
 
 
 @pytest.mark.parametrize("route", list(ROUTES))
@@ -163,6 +191,11 @@ def test_golden_cases(gpu, name, route):
         assert ex.code == 2, ex  # UGX_E_UNSUPPORTED: outside the path's scope, rejected loudly
         pytest.skip("out of scope: %s" % ex)
     for case, data in G.cases(name):
+        if route == "two_pass":
+            rec, _ = sc.find_all(pat, data)
+            assert len(rec) == case["matches"]
+            G.check_list(case, data, rec)
+            continue
         t = sc.count_lines(pat, data)
         assert t.matches == case["lines"], (name, route, case["input"], "lines")
         if route == "stream_nl" and t.newlines:

@@ -108,6 +108,11 @@ struct ugx_scanner {
   bool force_generic = false; // tests: always take the generic line-scan kernel
   bool legacy_any = false;    // tests / A-B timing: the tile-synchronous count_lines_any kernel instead of the streaming one
   bool count_newlines = false; // the streaming count also counts newlines
+  bool two_pass_records = false; // records by count pass + emit pass (A/B against the single-pass staging form)
+  uint64_t* tile_base = nullptr;  // staging base of every tile's records
+  uint64_t tile_base_cap = 0;
+  ugx_match* rec_stage = nullptr; // records in tile completion order
+  uint64_t rec_stage_cap = 0;
   bool no_pipeline = false;    // host buffers: one copy, then the scan (A/B timing of the overlapped path)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_copy = nullptr;
@@ -330,6 +335,8 @@ void ugx_scanner_destroy(ugx_scanner* s)
   cudaFree(s->totals);
   cudaFreeHost(s->h_totals);
   cudaFree(s->region_sum);
+  cudaFree(s->tile_base);
+  cudaFree(s->rec_stage);
   cudaFree(s->partials);
   cudaFree(s->ticket);
   cudaFree(s->records);
@@ -464,7 +471,7 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
   if (rc == UGX_OK)
     rc = ensure(s->tile_newlines, cap2, ntiles);
   s->tiles_cap = cap1 < cap2 ? cap1 : cap2;
-  if (rc == UGX_OK && want_records)
+  if (rc == UGX_OK && want_records && s->two_pass_records)
     rc = ensure(s->strip_counts, s->strips_cap, nstrips);
   if (rc != UGX_OK)
     return rc;
@@ -474,7 +481,7 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
   a.ntiles = ntiles;
   a.tile_matches = s->tile_matches;
   a.tile_newlines = s->tile_newlines;
-  a.strip_counts = want_records ? s->strip_counts : nullptr;
+  a.strip_counts = want_records && s->two_pass_records ? s->strip_counts : nullptr;
   a.out = nullptr;
   a.out_cap = 0;
   a.base_offset = base_offset;
@@ -541,6 +548,51 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
     tt.launches = 1;
     tt.kernel = UGX_K_TILE_ANY;
   }
+  else if (want_records && !s->two_pass_records)
+  {
+    // single-pass records: staging pass (tiles in completion order) + prefix + reorder into input order.  The staging
+    // capacity is a guess (the last result, or one record per 96 bytes); the cursor tells the exact need, so a
+    // second staging pass always fits.
+    rc = ensure(s->tile_base, s->tile_base_cap, ntiles);
+    uint64_t guess = s->records_n + s->records_n / 4 + n / 96 + 1024;
+    if (rc == UGX_OK && s->rec_stage_cap < guess)
+      rc = ensure(s->rec_stage, s->rec_stage_cap, guess);
+    if (rc != UGX_OK)
+      return rc;
+    unsigned long long* cursor = s->totals + 2;
+    uint64_t nrec = 0;
+    for (int attempt = 0; attempt < 2; ++attempt)
+    {
+      CU(ugx::launch_scan_records(p->dev, a, s->tile_base, s->rec_stage, s->rec_stage_cap, cursor, s->sm_count, s->stream));
+      CU(ugx::launch_tile_prefix(s->tile_matches, s->tile_newlines, ntiles, s->totals, s->stream));
+      CU(cudaMemcpyAsync(s->h_totals, s->totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+      CU(cudaStreamSynchronize(s->stream));
+      tt.launches += 2;
+      nrec = s->h_totals[0];
+      if (nrec <= s->rec_stage_cap)
+        break;
+      if (attempt == 1)
+        return fail(UGX_E_CUDA, "record staging overflowed twice");
+      rc = ensure(s->rec_stage, s->rec_stage_cap, nrec);
+      if (rc != UGX_OK)
+        return rc;
+    }
+    rc = ensure(s->records, s->records_cap, nrec);
+    if (rc != UGX_OK)
+      return rc;
+    if (nrec > 0)
+    {
+      CU(ugx::launch_reorder_records(s->rec_stage, s->records, s->tile_matches, s->tile_newlines, s->tile_base, ntiles,
+                                     s->totals, base_line, s->sm_count, s->stream));
+      tt.launches += 1;
+    }
+    tt.kernel = UGX_K_RECORDS;
+    s->records_n = nrec;
+    if (n_out)
+      *n_out = nrec;
+    if (dev_out)
+      *dev_out = s->records;
+  }
   else
   {
     CU(ugx::launch_scan_lines(p->dev, a, mode, false, s->sm_count, s->stream));
@@ -548,8 +600,9 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
     tt.launches = 2;
     tt.kernel = UGX_K_LINE_SCAN;
   }
-  CU(cudaMemcpyAsync(s->h_totals, s->totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
-  if (want_records)
+  if (!(want_records && !s->two_pass_records))
+    CU(cudaMemcpyAsync(s->h_totals, s->totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+  if (want_records && s->two_pass_records)
   {
     CU(cudaStreamSynchronize(s->stream));
     const uint64_t nrec = s->h_totals[0];
@@ -631,6 +684,7 @@ const char* ugx_kernel_name(uint32_t id)
     case UGX_K_STREAM_DFA: return "count_lines_stream_kernel";
     case UGX_K_TILE_ANY: return "count_lines_any_kernel";
     case UGX_K_LINE_SCAN: return "scan_lines_kernel";
+    case UGX_K_RECORDS: return "scan_records_kernel";
     default: return "none";
   }
 }
@@ -647,6 +701,11 @@ int ugx_scanner_set_option(ugx_scanner* s, const char* name, int value)
   if (strcmp(name, "legacy_any") == 0)
   {
     s->legacy_any = value != 0;
+    return UGX_OK;
+  }
+  if (strcmp(name, "two_pass_records") == 0)
+  {
+    s->two_pass_records = value != 0;
     return UGX_OK;
   }
   if (strcmp(name, "no_pipeline") == 0)

@@ -70,6 +70,13 @@ bool count_lines_literal_eligible(const DevPattern& P);
 cudaError_t launch_count_lines_literal(const DevPattern& P, const uint8_t* buf, uint64_t n, const StreamArgs& a, bool want_nl,
                                        int sm_count, cudaStream_t st);
 
+// single-pass records (records_kernel.cu): staging pass + reorder into input order
+cudaError_t launch_scan_records(const DevPattern& P, const ScanArgs& a, uint64_t* tile_base, ugx_match* stage_out,
+                                uint64_t stage_cap, unsigned long long* cursor, int sm_count, cudaStream_t st);
+cudaError_t launch_reorder_records(const ugx_match* stage, ugx_match* out, const uint64_t* pm, const uint64_t* pn,
+                                   const uint64_t* tile_base, uint64_t ntiles, const unsigned long long* totals,
+                                   uint64_t base_line, int sm_count, cudaStream_t st);
+
 cudaError_t launch_tile_prefix(uint64_t* tile_matches, uint64_t* tile_newlines, uint64_t ntiles,
                                unsigned long long* totals, cudaStream_t st);
 
