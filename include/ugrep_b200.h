@@ -136,7 +136,7 @@ typedef struct ugx_totals {
 
 /* scan kernels (reported in ugx_totals.kernel) */
 enum { UGX_K_NONE = 0, UGX_K_STREAM_LITERAL = 1, UGX_K_STREAM_DFA = 2, UGX_K_TILE_ANY = 3, UGX_K_LINE_SCAN = 4,
-       UGX_K_RECORDS = 5 };
+       UGX_K_RECORDS = 5, UGX_K_NEWLINES = 6 };
 
 const char *ugx_last_error(void);
 const char *ugx_kernel_name(uint32_t id);

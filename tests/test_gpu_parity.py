@@ -272,3 +272,17 @@ def test_pipelined_host_buffer_equals_device_scan(gpu):
         sc.set_option("no_pipeline", 0)
         if pname == "c2":
             assert got.matches == reps * op.count_lines(block)
+
+
+def test_count_newlines(gpu):
+    """ugx_count_newlines = reflex::nlcount: every length around the 16-byte vectors, device and host buffers"""
+    import torch
+    api, sc = gpu
+    base = corpus.block("c5", 300000)
+    for n in list(range(0, 70)) + [255, 256, 257, 4095, 4096, 4097, 65535, 65536, 65537, len(base)]:
+        data = base[:n]
+        assert sc.count_newlines(data).newlines == int((data == 10).sum()), n
+    big = np.tile(corpus.block("c1", 1 << 20), 40)
+    assert sc.count_newlines(torch.from_numpy(big).cuda()).newlines == int((big == 10).sum())
+    tricky = np.frombuffer(b"\n\x0b\n\x0b\x0a\x8a\x0a\xff\n" * 1000, dtype=np.uint8)  # bytes one off '\n', high bits set
+    assert sc.count_newlines(tricky).newlines == int((tricky == 10).sum())

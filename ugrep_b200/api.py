@@ -171,6 +171,13 @@ class Scanner:
         _check(lib().ugx_count_matches(self._h, pattern._h, C.c_void_p(ptr), n, C.byref(t)))
         return self._totals(t)
 
+    def count_newlines(self, data) -> Totals:
+        """reflex::nlcount over the buffer (totals.newlines)"""
+        ptr, n, keep = _buffer(data)
+        t = _Totals()
+        _check(lib().ugx_count_newlines(self._h, C.c_void_p(ptr), n, C.byref(t)))
+        return self._totals(t)
+
     def find_all_device(self, pattern: Pattern, data, base_offset: int = 0, base_line: int = 0) -> Totals:
         """Like find_all but the records stay on the device (fetch() copies a range to the host)."""
         ptr, n, keep = _buffer(data)

@@ -685,6 +685,7 @@ const char* ugx_kernel_name(uint32_t id)
     case UGX_K_TILE_ANY: return "count_lines_any_kernel";
     case UGX_K_LINE_SCAN: return "scan_lines_kernel";
     case UGX_K_RECORDS: return "scan_records_kernel";
+    case UGX_K_NEWLINES: return "count_newlines_kernel";
     default: return "none";
   }
 }
@@ -742,11 +743,33 @@ int ugx_scanner_fetch(ugx_scanner* s, ugx_match* out, uint64_t first, uint64_t c
 
 int ugx_count_newlines(ugx_scanner* s, const void* buf, uint64_t nbytes, ugx_totals* totals)
 {
-  (void)s;
-  (void)buf;
-  (void)nbytes;
-  (void)totals;
-  return fail(UGX_E_UNSUPPORTED, "ugx_count_newlines: not built yet");
+  if (s == nullptr || (buf == nullptr && nbytes != 0))
+    return fail(UGX_E_INVALID, "null argument");
+  ugx_totals tt;
+  memset(&tt, 0, sizeof(tt));
+  if (nbytes != 0)
+  {
+    CU(cudaSetDevice(s->device));
+    const uint8_t* dbuf = nullptr;
+    uint64_t h2d = 0;
+    const int rc = resolve(s, buf, nbytes, &dbuf, &h2d);
+    if (rc != UGX_OK)
+      return rc;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    CU(ugx::launch_count_newlines(dbuf, nbytes, s->totals + 1, s->sm_count, s->stream));
+    CU(cudaMemcpyAsync(s->h_totals + 1, s->totals + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaEventRecord(s->ev1, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    tt.newlines = s->h_totals[1];
+    tt.kernel_ms = ms;
+    tt.launches = 1;
+    tt.kernel = UGX_K_NEWLINES;
+  }
+  if (totals)
+    *totals = tt;
+  return UGX_OK;
 }
 
 } // extern "C"

@@ -77,6 +77,9 @@ cudaError_t launch_reorder_records(const ugx_match* stage, ugx_match* out, const
                                    const uint64_t* tile_base, uint64_t ntiles, const unsigned long long* totals,
                                    uint64_t base_line, int sm_count, cudaStream_t st);
 
+// reflex::nlcount (newline_count.cu)
+cudaError_t launch_count_newlines(const uint8_t* buf, uint64_t n, unsigned long long* total, int sm_count, cudaStream_t st);
+
 cudaError_t launch_tile_prefix(uint64_t* tile_matches, uint64_t* tile_newlines, uint64_t ntiles,
                                unsigned long long* totals, cudaStream_t st);
 
