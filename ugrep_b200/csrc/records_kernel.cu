@@ -49,7 +49,7 @@ __device__ __forceinline__ uint64_t line_last(const uint32_t* s_nl, const uint8_
 } // namespace
 
 template <bool HAS_META>
-__global__ void __launch_bounds__(SCAN_THREADS, 2)
+__global__ void __launch_bounds__(SCAN_THREADS, 3)
 scan_records_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, uint64_t ntiles,
                     uint32_t stage_table, uint64_t* __restrict__ tile_matches, uint64_t* __restrict__ tile_newlines,
                     uint64_t* __restrict__ tile_base_out, ugx_match* __restrict__ stage_out, uint64_t stage_cap,

@@ -25,7 +25,10 @@ namespace {
 
 // MODE 0: count matching lines (ugrep -c), 1: count matches (ugrep -c -o) / emit records (ugrep -o)
 template <int MODE, bool EMIT, bool HAS_META>
-__global__ void __launch_bounds__(SCAN_THREADS, 2)
+#ifndef UGX_SCAN_MINB
+#define UGX_SCAN_MINB 3
+#endif
+__global__ void __launch_bounds__(SCAN_THREADS, UGX_SCAN_MINB)
 scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, uint64_t ntiles,
                   uint32_t stage_table, uint64_t* __restrict__ tile_matches, uint64_t* __restrict__ tile_newlines,
                   uint32_t* __restrict__ strip_counts, ugx_match* __restrict__ out, uint64_t out_cap,
