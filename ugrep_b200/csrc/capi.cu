@@ -464,7 +464,8 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
     rc = resolve(s, buf, n, &dbuf, &h2d);
   if (rc != UGX_OK)
     return rc;
-  const uint64_t ntiles = (n + ugx::SCAN_TILE - 1) / ugx::SCAN_TILE;
+  const uint64_t tile_bytes = ugx::scan_tile_bytes(p->dev);
+  const uint64_t ntiles = (n + tile_bytes - 1) / tile_bytes;
   const uint64_t nstrips = (n + ugx::SCAN_STRIP - 1) / ugx::SCAN_STRIP;
   uint64_t cap1 = s->tiles_cap, cap2 = s->tiles_cap;
   rc = ensure(s->tile_matches, cap1, ntiles);

@@ -30,17 +30,18 @@ struct StagedRec {
 
 // end of the line that starts at tile offset `off`: the next newline in the tile's bitmap, else walk on in global
 // memory; the last byte of the buffer if there is none
+template <uint32_t TILE>
 __device__ __forceinline__ uint64_t line_last(const uint32_t* s_nl, const uint8_t* __restrict__ buf, uint64_t n,
                                               uint64_t tile_base, uint32_t off)
 {
-  constexpr uint32_t NW = SCAN_TILE / 32;
+  constexpr uint32_t NW = TILE / 32;
   uint32_t wi = off >> 5;
   uint32_t word = s_nl[wi] & (0xffffffffu << (off & 31));
   while (word == 0 && ++wi < NW)
     word = s_nl[wi];
   if (word != 0)
     return tile_base + (wi << 5) + (__ffs(word) - 1);
-  uint64_t p = tile_base + SCAN_TILE;
+  uint64_t p = tile_base + TILE;
   while (p < n && __ldg(buf + p) != '\n')
     ++p;
   return p < n ? p : n - 1;
@@ -48,13 +49,14 @@ __device__ __forceinline__ uint64_t line_last(const uint32_t* s_nl, const uint8_
 
 } // namespace
 
-template <bool HAS_META>
-__global__ void __launch_bounds__(SCAN_THREADS, 3)
+template <bool HAS_META, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS > 256 ? 2 : 3)
 scan_records_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, uint64_t ntiles,
                     uint32_t stage_table, uint64_t* __restrict__ tile_matches, uint64_t* __restrict__ tile_newlines,
                     uint64_t* __restrict__ tile_base_out, ugx_match* __restrict__ stage_out, uint64_t stage_cap,
                     unsigned long long* __restrict__ cursor, uint64_t base_offset)
 {
+  constexpr uint32_t TILE = THREADS * SCAN_STRIP;
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t warp_sums[33];
   __shared__ unsigned long long s_base;
@@ -62,9 +64,9 @@ scan_records_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restr
   uint8_t* s_pred = smem + 256;
   uint8_t* s_tap = s_pred + UGX_HASH;
   uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_tap + UGX_BTAP);
-  uint32_t* s_nl = s_cand + SCAN_TILE / 32;
-  StagedRec* s_rec = reinterpret_cast<StagedRec*>(s_nl + SCAN_TILE / 32);
-  uint16_t* s_next = reinterpret_cast<uint16_t*>(s_rec + SCAN_THREADS * REC_K);
+  uint32_t* s_nl = s_cand + TILE / 32;
+  StagedRec* s_rec = reinterpret_cast<StagedRec*>(s_nl + TILE / 32);
+  uint16_t* s_next = reinterpret_cast<uint16_t*>(s_rec + THREADS * REC_K);
   for (uint32_t i = threadIdx.x; i < 256 / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(s_cls)[i] = __ldg(reinterpret_cast<const uint32_t*>(P.cls) + i);
   for (uint32_t i = threadIdx.x; i < UGX_HASH / 16; i += blockDim.x)
@@ -84,12 +86,12 @@ scan_records_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restr
 
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
   {
-    const uint64_t tile_base = tile * SCAN_TILE;
+    const uint64_t tile_base = tile * TILE;
     const uint64_t s0 = tile_base + static_cast<uint64_t>(threadIdx.x) * SCAN_STRIP;
-    tile_phase_a<SCAN_TILE / 16 / SCAN_THREADS>(t, P, T, tile_base, reinterpret_cast<uint16_t*>(s_cand),
+    tile_phase_a<TILE / 16 / THREADS>(t, P, T, tile_base, reinterpret_cast<uint16_t*>(s_cand),
                                                 reinterpret_cast<uint16_t*>(s_nl));
     __syncthreads();
-    const CandMap cm{s_cand, tile_base, SCAN_TILE};
+    const CandMap cm{s_cand, tile_base, TILE};
     const uint64_t nl = (static_cast<uint64_t>(s_nl[2 * threadIdx.x + 1]) << 32) | s_nl[2 * threadIdx.x];
     uint64_t starts = nl << 1;
     if (s0 < n && (s0 == 0 || __ldg(buf + s0 - 1) == '\n'))
@@ -146,7 +148,7 @@ scan_records_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restr
         const uint32_t bit = __ffsll(static_cast<long long>(rest)) - 1;
         rest &= rest - 1;
         const uint32_t off = threadIdx.x * SCAN_STRIP + bit;
-        const uint64_t last = line_last(s_nl, buf, n, tile_base, off);
+        const uint64_t last = line_last<TILE>(s_nl, buf, n, tile_base, off);
         const uint32_t rel_line = nl_before + __popcll(nl & ((1ull << bit) - 1));
         Cursor m;
         set_current(t, m, tile_base + off);
@@ -206,20 +208,36 @@ reorder_records_kernel(const ugx_match* __restrict__ stage, ugx_match* __restric
   }
 }
 
-static size_t records_smem_bytes(const DevPattern& P, bool stage)
+static size_t records_smem_bytes(const DevPattern& P, bool stage, int threads)
 {
-  return 256 + UGX_HASH + UGX_BTAP + 2 * (SCAN_TILE / 8) + SCAN_THREADS * REC_K * sizeof(StagedRec) +
+  return 256 + UGX_HASH + UGX_BTAP + 2 * (threads * SCAN_STRIP / 8) + threads * REC_K * sizeof(StagedRec) +
          (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
+}
+
+template <bool HAS_META, int THREADS>
+static cudaError_t launch_records_one(const DevPattern& P, const ScanArgs& a, bool stage, int grid, size_t smem,
+                                      uint64_t* tile_base, ugx_match* stage_out, uint64_t stage_cap,
+                                      unsigned long long* cursor, cudaStream_t st)
+{
+  auto kern = scan_records_kernel<HAS_META, THREADS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess)
+    return e;
+  kern<<<grid, THREADS, smem, st>>>(P, a.buf, a.n, a.ntiles, stage ? 1u : 0u, a.tile_matches, a.tile_newlines, tile_base,
+                                    stage_out, stage_cap, cursor, a.base_offset);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_scan_records(const DevPattern& P, const ScanArgs& a, uint64_t* tile_base, ugx_match* stage_out,
                                 uint64_t stage_cap, unsigned long long* cursor, int sm_count, cudaStream_t st)
 {
-  const bool stage = P.has_meta == 0 && records_smem_bytes(P, true) <= 227 * 1024 - 2048;
-  const size_t smem = records_smem_bytes(P, stage);
+  const int threads = scan_threads(P); // the tile size must agree with scan_tile_bytes(): the caller sized ntiles by it
+  const bool stage = P.has_meta == 0 && P.table_bytes <= SCAN_MAX_SMEM_TABLE &&
+                     records_smem_bytes(P, true, threads) <= 227 * 1024 - 2048;
+  const size_t smem = records_smem_bytes(P, stage, threads);
   int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
-  if (per_sm > 2048 / SCAN_THREADS)
-    per_sm = 2048 / SCAN_THREADS;
+  if (per_sm > 2048 / threads)
+    per_sm = 2048 / threads;
   if (per_sm < 1)
     per_sm = 1;
   uint64_t g = static_cast<uint64_t>(sm_count) * per_sm;
@@ -230,27 +248,12 @@ cudaError_t launch_scan_records(const DevPattern& P, const ScanArgs& a, uint64_t
   cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st);
   if (e != cudaSuccess)
     return e;
+  const int grid = static_cast<int>(g);
   if (P.has_meta)
-  {
-    auto kern = scan_records_kernel<true>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess)
-      return e;
-    kern<<<static_cast<int>(g), SCAN_THREADS, smem, st>>>(P, a.buf, a.n, a.ntiles, stage ? 1u : 0u, a.tile_matches,
-                                                          a.tile_newlines, tile_base, stage_out, stage_cap, cursor,
-                                                          a.base_offset);
-  }
-  else
-  {
-    auto kern = scan_records_kernel<false>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess)
-      return e;
-    kern<<<static_cast<int>(g), SCAN_THREADS, smem, st>>>(P, a.buf, a.n, a.ntiles, stage ? 1u : 0u, a.tile_matches,
-                                                          a.tile_newlines, tile_base, stage_out, stage_cap, cursor,
-                                                          a.base_offset);
-  }
-  return cudaGetLastError();
+    return launch_records_one<true, 256>(P, a, stage, grid, smem, tile_base, stage_out, stage_cap, cursor, st);
+  if (threads == 512)
+    return launch_records_one<false, 512>(P, a, stage, grid, smem, tile_base, stage_out, stage_cap, cursor, st);
+  return launch_records_one<false, 256>(P, a, stage, grid, smem, tile_base, stage_out, stage_cap, cursor, st);
 }
 
 cudaError_t launch_reorder_records(const ugx_match* stage, ugx_match* out, const uint64_t* pm, const uint64_t* pn,

@@ -24,16 +24,18 @@ namespace {
 } // namespace
 
 // MODE 0: count matching lines (ugrep -c), 1: count matches (ugrep -c -o) / emit records (ugrep -o)
-template <int MODE, bool EMIT, bool HAS_META>
+template <int MODE, bool EMIT, bool HAS_META, int THREADS>
 #ifndef UGX_SCAN_MINB
 #define UGX_SCAN_MINB 3
 #endif
-__global__ void __launch_bounds__(SCAN_THREADS, UGX_SCAN_MINB)
+__global__ void __launch_bounds__(THREADS, THREADS > 256 ? 2 : UGX_SCAN_MINB)
 scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, uint64_t ntiles,
                   uint32_t stage_table, uint64_t* __restrict__ tile_matches, uint64_t* __restrict__ tile_newlines,
                   uint32_t* __restrict__ strip_counts, ugx_match* __restrict__ out, uint64_t out_cap,
                   uint64_t base_offset, uint64_t base_line)
 {
+  constexpr uint32_t TILE = THREADS * SCAN_STRIP;          // bytes per CTA iteration
+  constexpr uint32_t LINE_CAP = THREADS * 4;               // line starts per tile the dense line list holds
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t warp_sums[33];
   // ---- stage the tables: class map, predictor, bitap pairs, and the transition table when it fits ----
@@ -41,9 +43,9 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
   uint8_t* s_pred = smem + 256;
   uint8_t* s_tap = s_pred + UGX_HASH;
   uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_tap + UGX_BTAP);
-  uint32_t* s_nl = s_cand + SCAN_TILE / 32;
-  uint16_t* s_lines = reinterpret_cast<uint16_t*>(s_nl + SCAN_TILE / 32);
-  uint16_t* s_next = s_lines + SCAN_LINE_CAP;
+  uint32_t* s_nl = s_cand + TILE / 32;
+  uint16_t* s_lines = reinterpret_cast<uint16_t*>(s_nl + TILE / 32);
+  uint16_t* s_next = s_lines + LINE_CAP;
   for (uint32_t i = threadIdx.x; i < 256 / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(s_cls)[i] = __ldg(reinterpret_cast<const uint32_t*>(P.cls) + i);
   for (uint32_t i = threadIdx.x; i < UGX_HASH / 16; i += blockDim.x)
@@ -63,13 +65,13 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
 
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
   {
-    const uint64_t tile_base = tile * SCAN_TILE;
+    const uint64_t tile_base = tile * TILE;
     const uint64_t s0 = tile_base + static_cast<uint64_t>(threadIdx.x) * SCAN_STRIP;
     // ---- phase A: candidate and newline bitmaps of the tile (position-parallel prefilter)
-    tile_phase_a<SCAN_TILE / 16 / SCAN_THREADS>(t, P, T, tile_base, reinterpret_cast<uint16_t*>(s_cand),
+    tile_phase_a<TILE / 16 / THREADS>(t, P, T, tile_base, reinterpret_cast<uint16_t*>(s_cand),
                                                 reinterpret_cast<uint16_t*>(s_nl));
     __syncthreads();
-    const CandMap cm{s_cand, tile_base, SCAN_TILE};
+    const CandMap cm{s_cand, tile_base, TILE};
     // ---- newline mask of my strip and the line starts in it ----
     const uint64_t nl = (static_cast<uint64_t>(s_nl[2 * threadIdx.x + 1]) << 32) | s_nl[2 * threadIdx.x];
     uint64_t starts = nl << 1;
@@ -101,7 +103,7 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
     {
       uint32_t total_lines;
       const uint32_t first_idx = block_excl_scan(static_cast<uint32_t>(__popcll(starts)), warp_sums, &total_lines);
-      if (total_lines <= SCAN_LINE_CAP)
+      if (total_lines <= LINE_CAP)
       {
         dense = true;
         uint32_t idx = first_idx;
@@ -113,7 +115,7 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
           s_lines[idx++] = static_cast<uint16_t>(threadIdx.x * SCAN_STRIP + bit);
         }
         __syncthreads();
-        constexpr uint32_t NW = SCAN_TILE / 32;
+        constexpr uint32_t NW = TILE / 32;
         for (uint32_t i = threadIdx.x; i < total_lines; i += blockDim.x)
         {
           const uint32_t off = s_lines[i];
@@ -129,7 +131,7 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
               last = tile_base + (wi << 5) + (__ffs(word) - 1);
             else
             {
-              uint64_t p = tile_base + SCAN_TILE;
+              uint64_t p = tile_base + TILE;
               while (p < n && __ldg(buf + p) != '\n')
                 ++p;
               last = p < n ? p : n - 1;
@@ -215,7 +217,7 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
         tm += __shfl_down_sync(0xffffffffu, tm, d);
         tn += __shfl_down_sync(0xffffffffu, tn, d);
       }
-      __shared__ uint32_t red_m[SCAN_THREADS / 32], red_n[SCAN_THREADS / 32];
+      __shared__ uint32_t red_m[THREADS / 32], red_n[THREADS / 32];
       if ((threadIdx.x & 31) == 0)
       {
         red_m[threadIdx.x >> 5] = tm;
@@ -285,19 +287,27 @@ tile_prefix_kernel(uint64_t* __restrict__ tile_matches, uint64_t* __restrict__ t
 
 // ---- launchers ----
 
-static size_t scan_smem_bytes(const DevPattern& P, bool stage)
+static size_t scan_smem_bytes(const DevPattern& P, bool stage, int threads)
 {
-  return 256 + UGX_HASH + UGX_BTAP + 2 * (SCAN_TILE / 8) + 2 * SCAN_LINE_CAP + (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
+  return 256 + UGX_HASH + UGX_BTAP + 2 * (threads * SCAN_STRIP / 8) + 2 * (threads * 4) + (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
 }
 
-template <int MODE, bool EMIT, bool HAS_META>
+// CTA size: a staged table of more than 40 KiB leaves room for two CTAs per SM at most — make them 512 threads
+int scan_threads(const DevPattern& P)
+{
+  return (P.has_meta == 0 && P.table_bytes <= SCAN_MAX_SMEM_TABLE && P.table_bytes > 40 * 1024) ? 512 : 256;
+}
+
+uint32_t scan_tile_bytes(const DevPattern& P) { return static_cast<uint32_t>(scan_threads(P)) * SCAN_STRIP; }
+
+template <int MODE, bool EMIT, bool HAS_META, int THREADS>
 static cudaError_t launch_one(const DevPattern& P, const ScanArgs& a, bool stage, int grid, size_t smem, cudaStream_t st)
 {
-  auto kern = scan_lines_kernel<MODE, EMIT, HAS_META>;
+  auto kern = scan_lines_kernel<MODE, EMIT, HAS_META, THREADS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess)
     return e;
-  kern<<<grid, SCAN_THREADS, smem, st>>>(P, a.buf, a.n, a.ntiles, stage ? 1u : 0u, a.tile_matches, a.tile_newlines,
+  kern<<<grid, THREADS, smem, st>>>(P, a.buf, a.n, a.ntiles, stage ? 1u : 0u, a.tile_matches, a.tile_newlines,
                                          a.strip_counts, a.out, a.out_cap, a.base_offset, a.base_line);
   return cudaGetLastError();
 }
@@ -305,11 +315,12 @@ static cudaError_t launch_one(const DevPattern& P, const ScanArgs& a, bool stage
 cudaError_t launch_scan_lines(const DevPattern& P, const ScanArgs& a, int mode, bool emit, int sm_count, cudaStream_t st)
 {
   const bool stage = P.has_meta == 0 && P.table_bytes <= SCAN_MAX_SMEM_TABLE;
-  const size_t smem = scan_smem_bytes(P, stage);
+  const int threads = scan_threads(P);
+  const size_t smem = scan_smem_bytes(P, stage, threads);
   // persistent grid: as many CTAs as fit per SM, times the SM count, capped by the number of tiles
   int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
-  if (per_sm > 2048 / SCAN_THREADS)
-    per_sm = 2048 / SCAN_THREADS;
+  if (per_sm > 2048 / threads)
+    per_sm = 2048 / threads;
   if (per_sm < 1)
     per_sm = 1;
   uint64_t g = static_cast<uint64_t>(sm_count) * per_sm;
@@ -319,11 +330,21 @@ cudaError_t launch_scan_lines(const DevPattern& P, const ScanArgs& a, int mode, 
     g = 1;
   const int grid = static_cast<int>(g);
   const bool meta = P.has_meta != 0;
+#define UGX_SCAN_GO(MODE, EMIT)                                                                                 \
+  do                                                                                                            \
+  {                                                                                                             \
+    if (meta)                                                                                                   \
+      return launch_one<MODE, EMIT, true, 256>(P, a, stage, grid, smem, st);                                    \
+    if (threads == 512)                                                                                         \
+      return launch_one<MODE, EMIT, false, 512>(P, a, stage, grid, smem, st);                                   \
+    return launch_one<MODE, EMIT, false, 256>(P, a, stage, grid, smem, st);                                     \
+  } while (0)
   if (mode == 0)
-    return meta ? launch_one<0, false, true>(P, a, stage, grid, smem, st) : launch_one<0, false, false>(P, a, stage, grid, smem, st);
+    UGX_SCAN_GO(0, false);
   if (!emit)
-    return meta ? launch_one<1, false, true>(P, a, stage, grid, smem, st) : launch_one<1, false, false>(P, a, stage, grid, smem, st);
-  return meta ? launch_one<1, true, true>(P, a, stage, grid, smem, st) : launch_one<1, true, false>(P, a, stage, grid, smem, st);
+    UGX_SCAN_GO(1, false);
+  UGX_SCAN_GO(1, true);
+#undef UGX_SCAN_GO
 }
 
 cudaError_t launch_tile_prefix(uint64_t* tile_matches, uint64_t* tile_newlines, uint64_t ntiles,

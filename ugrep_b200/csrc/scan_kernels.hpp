@@ -10,7 +10,7 @@ namespace ugx {
 
 struct DevPattern;
 
-constexpr int SCAN_THREADS = 256;                      // threads per CTA
+constexpr int SCAN_THREADS = 256;                      // threads per CTA (512 for big staged tables: scan_threads())
 constexpr int SCAN_STRIP = 64;                         // bytes per thread per tile
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_STRIP;   // bytes per CTA iteration (16 KiB)
 constexpr uint32_t SCAN_LINE_CAP = 1024;                // line starts per tile the dense line list holds
@@ -30,6 +30,9 @@ struct ScanArgs {
   uint64_t base_line;
 };
 
+// CTA size / tile size of the line-scan and records kernels for this pattern (ntiles = ceil(n / scan_tile_bytes))
+int scan_threads(const DevPattern& P);
+uint32_t scan_tile_bytes(const DevPattern& P);
 cudaError_t launch_scan_lines(const DevPattern& P, const ScanArgs& a, int mode, bool emit, int sm_count, cudaStream_t st);
 // `ugrep -c` for patterns without look-back: one position-parallel kernel, totals[0] = matching lines, [1] = newlines
 bool count_lines_any_eligible(const DevPattern& P);
