@@ -50,7 +50,7 @@ __device__ __forceinline__ uint64_t line_last(const uint32_t* s_nl, const uint8_
 } // namespace
 
 template <bool HAS_META, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS > 256 ? 2 : 3)
+__global__ void __launch_bounds__(THREADS, THREADS > 256 ? 2048 / THREADS : 8)
 scan_records_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, uint64_t ntiles,
                     uint32_t stage_table, uint64_t* __restrict__ tile_matches, uint64_t* __restrict__ tile_newlines,
                     uint64_t* __restrict__ tile_base_out, ugx_match* __restrict__ stage_out, uint64_t stage_cap,
@@ -251,8 +251,8 @@ cudaError_t launch_scan_records(const DevPattern& P, const ScanArgs& a, uint64_t
   const int grid = static_cast<int>(g);
   if (P.has_meta)
     return launch_records_one<true, 256>(P, a, stage, grid, smem, tile_base, stage_out, stage_cap, cursor, st);
-  if (threads == 512)
-    return launch_records_one<false, 512>(P, a, stage, grid, smem, tile_base, stage_out, stage_cap, cursor, st);
+  if (threads != 256)
+    return launch_records_one<false, 1024>(P, a, stage, grid, smem, tile_base, stage_out, stage_cap, cursor, st);
   return launch_records_one<false, 256>(P, a, stage, grid, smem, tile_base, stage_out, stage_cap, cursor, st);
 }
 

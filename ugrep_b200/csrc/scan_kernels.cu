@@ -26,9 +26,9 @@ namespace {
 // MODE 0: count matching lines (ugrep -c), 1: count matches (ugrep -c -o) / emit records (ugrep -o)
 template <int MODE, bool EMIT, bool HAS_META, int THREADS>
 #ifndef UGX_SCAN_MINB
-#define UGX_SCAN_MINB 3
+#define UGX_SCAN_MINB 8
 #endif
-__global__ void __launch_bounds__(THREADS, THREADS > 256 ? 2 : UGX_SCAN_MINB)
+__global__ void __launch_bounds__(THREADS, THREADS > 256 ? 2048 / THREADS : UGX_SCAN_MINB)
 scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, uint64_t ntiles,
                   uint32_t stage_table, uint64_t* __restrict__ tile_matches, uint64_t* __restrict__ tile_newlines,
                   uint32_t* __restrict__ strip_counts, ugx_match* __restrict__ out, uint64_t out_cap,
@@ -292,10 +292,14 @@ static size_t scan_smem_bytes(const DevPattern& P, bool stage, int threads)
   return 256 + UGX_HASH + UGX_BTAP + 2 * (threads * SCAN_STRIP / 8) + 2 * (threads * 4) + (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
 }
 
-// CTA size: a staged table of more than 40 KiB leaves room for two CTAs per SM at most — make them 512 threads
+#ifndef UGX_SCAN_BIG_THREADS
+#define UGX_SCAN_BIG_THREADS 1024
+#endif
+// CTA size: a staged table of more than 40 KiB leaves room for two CTAs per SM at most — make them big.  The find
+// loop is latency-bound (dependent byte loads, divergent branches): resident warps matter more than registers.
 int scan_threads(const DevPattern& P)
 {
-  return (P.has_meta == 0 && P.table_bytes <= SCAN_MAX_SMEM_TABLE && P.table_bytes > 40 * 1024) ? 512 : 256;
+  return (P.has_meta == 0 && P.table_bytes <= SCAN_MAX_SMEM_TABLE && P.table_bytes > 40 * 1024) ? UGX_SCAN_BIG_THREADS : 256;
 }
 
 uint32_t scan_tile_bytes(const DevPattern& P) { return static_cast<uint32_t>(scan_threads(P)) * SCAN_STRIP; }
@@ -335,8 +339,8 @@ cudaError_t launch_scan_lines(const DevPattern& P, const ScanArgs& a, int mode, 
   {                                                                                                             \
     if (meta)                                                                                                   \
       return launch_one<MODE, EMIT, true, 256>(P, a, stage, grid, smem, st);                                    \
-    if (threads == 512)                                                                                         \
-      return launch_one<MODE, EMIT, false, 512>(P, a, stage, grid, smem, st);                                   \
+    if (threads != 256)                                                                                         \
+      return launch_one<MODE, EMIT, false, UGX_SCAN_BIG_THREADS>(P, a, stage, grid, smem, st);                                   \
     return launch_one<MODE, EMIT, false, 256>(P, a, stage, grid, smem, st);                                     \
   } while (0)
   if (mode == 0)
