@@ -286,3 +286,27 @@ def test_count_newlines(gpu):
     assert sc.count_newlines(torch.from_numpy(big).cuda()).newlines == int((big == 10).sum())
     tricky = np.frombuffer(b"\n\x0b\n\x0b\x0a\x8a\x0a\xff\n" * 1000, dtype=np.uint8)  # bytes one off '\n', high bits set
     assert sc.count_newlines(tricky).newlines == int((tricky == 10).sum())
+
+
+def test_misaligned_device_pointers_and_random_slices(gpu):
+    """device buffers that do not start on a 16-byte boundary (views into a larger tensor) and random slices that cut
+    lines anywhere: every mode against the oracle"""
+    import torch
+    api, sc = gpu
+    rng = np.random.default_rng(11)
+    for pname, cname in (("c1", "c1"), ("c2", "c2"), ("c4", "c4"), ("c5", "c5"), ("c3b", "c3")):
+        path = os.path.join(PAT_DIR, pname + ".ugxp")
+        pat = api.Pattern.load(path, 0)
+        op = O.OraclePattern(path)
+        base = corpus.block(cname, 400000)
+        dev = torch.from_numpy(base).cuda()
+        for _ in range(6):
+            lo = int(rng.integers(0, 50000))
+            hi = int(rng.integers(lo + 1, len(base)))
+            data = base[lo:hi]
+            view = dev[lo:hi]
+            assert sc.count_lines(pat, view).matches == op.count_lines(data), (pname, lo, hi)
+            assert sc.count_matches(pat, view).matches == op.count_matches(data), (pname, lo, hi)
+            rec, _ = sc.find_all(pat, view)
+            assert same(rec, op.find_all(data)), (pname, lo, hi)
+            assert sc.count_newlines(view).newlines == int((data == 10).sum())
