@@ -14,6 +14,7 @@
 // A line belongs to the tile it starts in; the one line that runs past the end of the tile is
 // followed by the whole CTA ("tail scan") until it matches or ends.
 #include "device_pattern.cuh"
+#include "ptx.cuh"
 #include "line_match.cuh"
 #include "scan_kernels.hpp"
 #include "tile_phase_a.cuh"
@@ -93,15 +94,10 @@ count_lines_any_kernel(const __grid_constant__ DevPattern P, const uint8_t* __re
   int* s_lastnl = reinterpret_cast<int*>(s_line + NW);
   uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_lastnl + NW);
   uint16_t* s_next = s_queue + 32 * 64;
-  for (uint32_t i = threadIdx.x; i < 256 / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(s_cls)[i] = __ldg(reinterpret_cast<const uint32_t*>(P.cls) + i);
-  for (uint32_t i = threadIdx.x; i < UGX_HASH / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(s_pred)[i] = __ldg(reinterpret_cast<const uint4*>(P.pred) + i);
-  for (uint32_t i = threadIdx.x; i < UGX_BTAP / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(s_tap)[i] = __ldg(reinterpret_cast<const uint4*>(P.tap) + i);
-  if (stage_table)
-    for (uint32_t i = threadIdx.x; i < (P.table_bytes + 15) / 16; i += blockDim.x)
-      reinterpret_cast<uint4*>(s_next)[i] = __ldg(reinterpret_cast<const uint4*>(P.next) + i);
+  // tables -> shared memory by bulk asynchronous copies (ptx.cuh)
+  __shared__ __align__(8) uint64_t s_bar;
+  stage_tables_bulk(&s_bar, s_cls, P.cls, s_pred, P.pred, s_tap, P.tap, s_next, P.next,
+                    stage_table ? ((P.table_bytes + 15) / 16) * 16 : 0);
   if (threadIdx.x < 2)
     s_red[threadIdx.x] = 0;
   __syncthreads();

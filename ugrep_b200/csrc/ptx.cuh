@@ -69,4 +69,30 @@ __device__ __forceinline__ uint2 lds64(const void* p)
   return v;
 }
 
+// Stage a pattern's tables in shared memory with the bulk-copy engine: one thread issues up to four 1-D copies
+// against one mbarrier, every thread of the CTA waits on it.  All sizes are multiples of 16 bytes, all pointers
+// 16-byte aligned.  Call from every thread of the CTA, once per kernel (phase 0 of `bar`).
+__device__ __forceinline__ void stage_tables_bulk(uint64_t* bar, void* s_cls, const void* g_cls, void* s_pred, const void* g_pred,
+                                                  void* s_tap, const void* g_tap, void* s_next, const void* g_next,
+                                                  uint32_t next_bytes)
+{
+  if (threadIdx.x == 0)
+  {
+    mbar_init(bar, 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    mbar_arrive_expect_tx(bar, 256 + 4096 + 2048 + next_bytes);
+    bulk_copy_g2s(s_cls, g_cls, 256, bar);
+    bulk_copy_g2s(s_pred, g_pred, 4096, bar);
+    bulk_copy_g2s(s_tap, g_tap, 2048, bar);
+    if (next_bytes != 0)
+      bulk_copy_g2s(s_next, g_next, next_bytes, bar);
+  }
+  mbar_wait(bar, 0);
+  __syncthreads();
+}
+
 } // namespace ugx

@@ -14,6 +14,7 @@
 // No ordering depends on an atomic: the cursor only assigns staging space.
 #include "block_scan.cuh"
 #include "device_pattern.cuh"
+#include "ptx.cuh"
 #include "line_match.cuh"
 #include "scan_kernels.hpp"
 #include "tile_phase_a.cuh"
@@ -67,15 +68,10 @@ scan_records_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restr
   uint32_t* s_nl = s_cand + TILE / 32;
   StagedRec* s_rec = reinterpret_cast<StagedRec*>(s_nl + TILE / 32);
   uint16_t* s_next = reinterpret_cast<uint16_t*>(s_rec + THREADS * REC_K);
-  for (uint32_t i = threadIdx.x; i < 256 / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(s_cls)[i] = __ldg(reinterpret_cast<const uint32_t*>(P.cls) + i);
-  for (uint32_t i = threadIdx.x; i < UGX_HASH / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(s_pred)[i] = __ldg(reinterpret_cast<const uint4*>(P.pred) + i);
-  for (uint32_t i = threadIdx.x; i < UGX_BTAP / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(s_tap)[i] = __ldg(reinterpret_cast<const uint4*>(P.tap) + i);
-  if (stage_table)
-    for (uint32_t i = threadIdx.x; i < (P.table_bytes + 15) / 16; i += blockDim.x)
-      reinterpret_cast<uint4*>(s_next)[i] = __ldg(reinterpret_cast<const uint4*>(P.next) + i);
+  // tables -> shared memory by bulk asynchronous copies (ptx.cuh)
+  __shared__ __align__(8) uint64_t s_bar;
+  stage_tables_bulk(&s_bar, s_cls, P.cls, s_pred, P.pred, s_tap, P.tap, s_next, P.next,
+                    stage_table ? ((P.table_bytes + 15) / 16) * 16 : 0);
   __syncthreads();
   Tables T;
   T.cls = s_cls;

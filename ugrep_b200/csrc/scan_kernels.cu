@@ -12,6 +12,7 @@
 // Records (ugrep -o) come from a second run of scan_lines_kernel that knows every strip's
 // output offset: deterministic input order, no atomics in the ordering.
 #include "device_pattern.cuh"
+#include "ptx.cuh"
 #include "line_match.cuh"
 #include "scan_kernels.hpp"
 #include "tile_phase_a.cuh"
@@ -46,15 +47,10 @@ scan_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restric
   uint32_t* s_nl = s_cand + TILE / 32;
   uint16_t* s_lines = reinterpret_cast<uint16_t*>(s_nl + TILE / 32);
   uint16_t* s_next = s_lines + LINE_CAP;
-  for (uint32_t i = threadIdx.x; i < 256 / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(s_cls)[i] = __ldg(reinterpret_cast<const uint32_t*>(P.cls) + i);
-  for (uint32_t i = threadIdx.x; i < UGX_HASH / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(s_pred)[i] = __ldg(reinterpret_cast<const uint4*>(P.pred) + i);
-  for (uint32_t i = threadIdx.x; i < UGX_BTAP / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(s_tap)[i] = __ldg(reinterpret_cast<const uint4*>(P.tap) + i);
-  if (stage_table)
-    for (uint32_t i = threadIdx.x; i < (P.table_bytes + 15) / 16; i += blockDim.x)
-      reinterpret_cast<uint4*>(s_next)[i] = __ldg(reinterpret_cast<const uint4*>(P.next) + i);
+  // tables -> shared memory by bulk asynchronous copies (ptx.cuh)
+  __shared__ __align__(8) uint64_t s_bar;
+  stage_tables_bulk(&s_bar, s_cls, P.cls, s_pred, P.pred, s_tap, P.tap, s_next, P.next,
+                    stage_table ? ((P.table_bytes + 15) / 16) * 16 : 0);
   __syncthreads();
   Tables T;
   T.cls = s_cls;

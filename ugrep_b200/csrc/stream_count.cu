@@ -25,6 +25,7 @@
 #include "device_pattern.cuh"
 #include "line_match.cuh"
 #include "scan_kernels.hpp"
+#include "ptx.cuh"
 #include "stream_common.cuh"
 #include "tile_phase_a.cuh"
 
@@ -322,12 +323,10 @@ count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* _
   uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_succ + 16 * NWARPS);
   uint32_t* s_h4 = reinterpret_cast<uint32_t*>(s_queue + 64 * NWARPS);
   uint16_t* s_next = reinterpret_cast<uint16_t*>(s_h4 + (a.use_h4 ? UGX_HASH : 0));
-  for (uint32_t i = threadIdx.x; i < 256 / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(s_cls)[i] = __ldg(reinterpret_cast<const uint32_t*>(P.cls) + i);
-  for (uint32_t i = threadIdx.x; i < UGX_HASH / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(s_pred)[i] = __ldg(reinterpret_cast<const uint4*>(P.pred) + i);
-  for (uint32_t i = threadIdx.x; i < UGX_BTAP / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(s_tap)[i] = __ldg(reinterpret_cast<const uint4*>(P.tap) + i);
+  // ---- tables -> shared memory by bulk asynchronous copies (cp.async.bulk, the TMA path without a tensor map)
+  __shared__ __align__(8) uint64_t s_bar;
+  stage_tables_bulk(&s_bar, s_cls, P.cls, s_pred, P.pred, s_tap, P.tap, s_next, P.next,
+                    a.stage_table ? ((P.table_bytes + 15) / 16) * 16 : 0);
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
     s_lut[i] = P.plan.pm2 ? (((__ldg(P.pred + i) >> 7) & 1u) | (((__ldg(P.pred + i) >> 6) & 1u) << 8)) : P.plan.lut[i];
   for (uint32_t i = threadIdx.x; i < 16 * NWARPS; i += blockDim.x)
@@ -345,9 +344,6 @@ count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* _
           v |= ((e >> (3 + tt)) & 1u) << (8 * tt);
       s_h4[i] = v;
     }
-  if (a.stage_table)
-    for (uint32_t i = threadIdx.x; i < (P.table_bytes + 15) / 16; i += blockDim.x)
-      reinterpret_cast<uint4*>(s_next)[i] = __ldg(reinterpret_cast<const uint4*>(P.next) + i);
   __syncthreads();
   Tables T;
   T.cls = s_cls;
