@@ -73,6 +73,51 @@ __device__ __noinline__ bool attempt_meta(const Text& t, const DevPattern& P, ui
   return m.cap != 0 && m.cur > m.txt;
 }
 
+// the same attempt when the first 8 text bytes at `pos` are already in registers (pos + 8 <= end)
+__device__ __forceinline__ bool attempt_table_first8(const Text& t, const DevPattern& P, const Tables& T, uint64_t pos,
+                                                     uint64_t first8)
+{
+  uint32_t state = 0;
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i)
+  {
+    const uint32_t ch = static_cast<uint32_t>(first8) & 0xffu;
+    first8 >>= 8;
+    const uint32_t nxt = T.next[state * P.ncls + T.cls[ch]];
+    if (nxt >= P.first_acc)
+    {
+      if (nxt == D_DEAD)
+        return false;
+      if (nxt < P.first_leaf)
+        return true;
+      return (__ldg(P.accept + nxt) & 0x7fffffffu) != 0;
+    }
+    if (nxt == 0 && P.acc0)
+      return true;
+    state = nxt;
+  }
+  // longer than 8 bytes: continue from text memory
+  uint64_t p = pos + 8;
+  for (;;)
+  {
+    if (p >= t.end)
+      return false;
+    const uint32_t ch = t.raw(p++);
+    const uint32_t nxt = T.next[state * P.ncls + T.cls[ch]];
+    if (nxt >= P.first_acc)
+    {
+      if (nxt == D_DEAD)
+        return false;
+      if (nxt < P.first_leaf)
+        return true;
+      return (__ldg(P.accept + nxt) & 0x7fffffffu) != 0;
+    }
+    if (nxt == 0 && P.acc0)
+      return true;
+    state = nxt;
+  }
+}
+
 template <int KIND>
 __device__ __forceinline__ bool attempt_at(const Text& t, const DevPattern& P, const Tables& T, uint64_t pos)
 {
@@ -87,7 +132,8 @@ __device__ __forceinline__ bool attempt_at(const Text& t, const DevPattern& P, c
 // instantiated 16 times (4 spans x watch/cruise x full/guarded) and must stay within the instruction cache.
 // the needle + hashed-predictor routines on an interior position (pos + 12 <= end): the 8 bytes the predicate reads
 // come from three aligned 32-bit loads instead of eight guarded byte loads
-__device__ __forceinline__ bool cand_pin_pmh_interior(const Text& t, const DevPattern& P, const Tables& T, uint64_t pos)
+__device__ __forceinline__ bool cand_pin_pmh_interior(const Text& t, const DevPattern& P, const Tables& T, uint64_t pos,
+                                                      uint64_t& first8)
 {
   const uint8_t* p = t.b + pos;
   const uint32_t sh = (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p)) & 3u) * 8;
@@ -95,6 +141,7 @@ __device__ __forceinline__ bool cand_pin_pmh_interior(const Text& t, const DevPa
   const uint32_t lo = __ldg(a), mid = __ldg(a + 1), hi = __ldg(a + 2);
   const uint32_t x = __funnelshift_r(lo, mid, sh), y = __funnelshift_r(mid, hi, sh);
   const uint64_t xy = (static_cast<uint64_t>(y) << 32) | x;
+  first8 = xy;
   const uint32_t ca = static_cast<uint32_t>(xy >> (8 * P.lcp)) & 0xffu, cb = static_cast<uint32_t>(xy >> (8 * P.lcs)) & 0xffu;
   if (P.adv == UGX_ADV_PIN1_PMH)
   {
@@ -123,7 +170,15 @@ __device__ __noinline__ bool stage2(Text t, const DevPattern& P, Tables T, uint6
     const bool pin_pmh = P.adv == UGX_ADV_PIN_PMH || P.adv == UGX_ADV_PIN1_PMH;
     if (pos + 12 <= t.end && (pin_pmh || P.adv == UGX_ADV_PMA))
     {
-      if (pin_pmh ? !cand_pin_pmh_interior(t, P, T, pos) : !cand_pma_interior(t, T, pos))
+      if (pin_pmh)
+      {
+        uint64_t first8;
+        if (!cand_pin_pmh_interior(t, P, T, pos, first8))
+          return false;
+        if (KIND != SK_META && !P.one)
+          return attempt_table_first8(t, P, T, pos, first8);
+      }
+      else if (!cand_pma_interior(t, T, pos))
         return false;
     }
     else if (!cand(t, P, T, pos))
@@ -273,21 +328,40 @@ struct DfaEval {
     }
     if (!__any_sync(0xffffffffu, surv != 0))
       return false;
-    // ---- compaction + balanced stage 2
+    // ---- compaction + balanced stage 2.  Per round: a warp scan of the lanes' survivor counts; the lanes whose
+    // survivors fit into the free part of the 64-entry queue write ALL of them (so a lane holding a run of
+    // survivors does not cost one round per survivor); full groups of 32 are then handed out one per lane.
     uint32_t qn = 0;
     while (__any_sync(0xffffffffu, surv != 0))
     {
-      const bool has = surv != 0;
-      const uint32_t b = __ballot_sync(0xffffffffu, has);
-      if (has)
+      const uint32_t cnt = __popc(surv);
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
       {
-        const uint32_t k = __ffs(surv) - 1;
-        surv &= surv - 1;
-        queue[qn + __popc(b & ((1u << lane) - 1))] = static_cast<uint16_t>(lane * 16 + k);
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= static_cast<uint32_t>(d))
+          incl += y;
       }
-      qn += __popc(b);
+      const uint32_t room = 64u - qn;
+      const bool fits = incl <= room; // monotone over lanes: a prefix of the lanes fits
+      if (fits)
+      {
+        uint32_t at = qn + incl - cnt;
+        while (surv != 0)
+        {
+          const uint32_t k = __ffs(surv) - 1;
+          surv &= surv - 1;
+          queue[at++] = static_cast<uint16_t>(lane * 16 + k);
+        }
+      }
+      const uint32_t fitmask = __ballot_sync(0xffffffffu, fits);
+      // entries written = inclusive count of the last fitting lane (at least one lane fits: cnt <= 16 <= room
+      // whenever qn < 32, which the flush below guarantees)
+      const uint32_t last_fit = 31u - __clz(fitmask);
+      qn += __shfl_sync(0xffffffffu, incl, last_fit);
       __syncwarp();
-      if (qn >= 32)
+      while (qn >= 32)
       {
         qn -= 32;
         try_at(sbase, queue[qn + lane], exact);
