@@ -121,6 +121,22 @@ enum {
   UGX_ADV_STRING, UGX_ADV_STRING_PMA, UGX_ADV_STRING_PMH
 };
 
+/* what the host-side export derives from a compiled pattern, without touching a device: the dense DFA's shape and the
+ * first-stage filter the position-parallel kernels use (csrc/filter_plan.hpp).  For tests and diagnostics. */
+typedef struct ugx_plan_info {
+  uint32_t states, classes, table_bytes;
+  uint32_t first_acc, first_leaf; /* state numbering: [1, first_acc) plain, [first_acc, first_leaf) accepting, rest leaves */
+  uint32_t max_match_len;         /* longest match in bytes, 0xffffffff = unbounded (cyclic DFA) */
+  uint32_t advance;               /* UGX_ADV_* */
+  uint32_t has_meta, newline_live;
+  uint32_t kind;                  /* 0 all survive, 2 two literal anchors, 3 byte-set terms */
+  uint32_t nterms, t_off[3];      /* byte-set terms: byte (k + t_off[t]) must not have bit 8*t set in lut[] */
+  uint32_t a_off[2], a_chr[2];    /* literal anchors: offsets and bytes */
+  uint32_t h4_terms, h4_shift;    /* hashed-predictor terms (steps 3.. of predict_match PMH) */
+  uint32_t pm2, pm2_shift;        /* PM4 two-byte term */
+  uint32_t lut[256];
+} ugx_plan_info;
+
 typedef struct ugx_pattern ugx_pattern; /* immutable once created; shareable between host threads */
 typedef struct ugx_scanner ugx_scanner; /* per host thread / per stream scratch (counters, record arena) */
 
@@ -146,6 +162,9 @@ int  ugx_abi_version(void);
 int  ugx_pattern_create(const uint32_t *opc, uint32_t nop, const ugx_prefilter *pf,
                         uint32_t matcher_flags, int device, ugx_pattern **out);
 int  ugx_pattern_load(const char *path, int device, ugx_pattern **out);
+/* host only (no device needed): DFA export + filter plan of a compiled pattern */
+int  ugx_plan_describe(const uint32_t *opc, uint32_t nop, const ugx_prefilter *pf, uint32_t matcher_flags,
+                       ugx_plan_info *out);
 int  ugx_pattern_info_get(const ugx_pattern *p, ugx_pattern_info *info);
 void ugx_pattern_destroy(ugx_pattern *p);
 

@@ -1,0 +1,115 @@
+"""CPU test of the host-side export (DFA flattening + first-stage filter plan, csrc/pattern_host.cpp) through the
+host-only entry point ugx_plan_describe: the plan must be a SUPERSET of the reference's candidate predicate on
+interior positions — the property that makes the two-stage evaluation of the position-parallel kernels exact.
+The reference predicate comes from the oracle (ora_candidates); stage 1 is simulated here with numpy from the
+tables the library reports, exactly as the kernels evaluate it (stream_count.cu / stream_literal.cu)."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import golden_lib as G
+import oracle_lib as O
+from ugrep_b200 import corpus
+
+LIB = os.path.join(O.ROOT, "ugrep_b200", "libugrep_b200.so")
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("states", "classes", "table_bytes", "first_acc", "first_leaf", "max_match_len",
+                                          "advance", "has_meta", "newline_live", "kind", "nterms")] + \
+               [("t_off", C.c_uint32 * 3), ("a_off", C.c_uint32 * 2), ("a_chr", C.c_uint32 * 2),
+                ("h4_terms", C.c_uint32), ("h4_shift", C.c_uint32), ("pm2", C.c_uint32), ("pm2_shift", C.c_uint32),
+                ("lut", C.c_uint32 * 256)]
+
+
+def load_ugxp(path):
+    b = open(path, "rb").read()
+    nop, regex_len, pf_size, flags = struct.unpack_from("<4I", b, 8)
+    pf = b[24:24 + pf_size]
+    opc = b[24 + pf_size:24 + pf_size + 4 * nop]
+    return opc, nop, pf, flags
+
+
+def describe(path):
+    lib = C.CDLL(LIB)
+    lib.ugx_last_error.restype = C.c_char_p
+    opc, nop, pf, flags = load_ugxp(path)
+    info = PlanInfo()
+    rc = lib.ugx_plan_describe(opc, nop, pf, flags, C.byref(info))
+    return rc, info, pf
+
+
+def stage1(info, pf, data):
+    """pass mask of the first stage for positions 0 .. n-25 (interior), as the kernels evaluate it"""
+    n = len(data)
+    m = n - 24
+    d = data.astype(np.uint32)
+    ok = np.ones(m, dtype=bool)
+    pma = np.frombuffer(pf, dtype=np.uint8, count=4096, offset=48 + 256 + 256 + 2048).astype(np.uint32)
+    pmh = np.frombuffer(pf, dtype=np.uint8, count=4096, offset=48 + 256 + 256 + 2048 + 4096).astype(np.uint32)
+    if info.kind == 2:
+        ok &= d[0:m] == info.a_chr[0]
+        ok &= d[info.a_off[1]:info.a_off[1] + m] == info.a_chr[1]
+        return ok, "anchor2"
+    used = []
+    if info.h4_terms:
+        g = np.zeros(n, dtype=np.uint32)
+        for back in range(4):  # g(p) = hash of bytes p-3 .. p
+            g[3:] ^= (d[3 - back:n - back] << (3 * back)) & 4095
+        for t in range(info.h4_terms):
+            p = np.arange(m) + info.h4_shift + 3 + t
+            ok &= ((pmh[g[p]] >> (3 + t)) & 1) == 0
+        used.append("h4x%d" % info.h4_terms)
+    elif info.pm2:
+        c0 = d[info.pm2_shift:info.pm2_shift + m]
+        c1 = d[info.pm2_shift + 1:info.pm2_shift + 1 + m]
+        a, b = pma[c0], pma[((c0 << 3) ^ c1) & 4095]
+        q7, q6, q5, q4 = (a >> 7) & 1, (a >> 6) & 1, (b >> 5) & 1, (b >> 4) & 1
+        ok &= (q7 & q5 & (q4 | q6)) == 0
+        used.append("pm2")
+    elif info.kind == 3:
+        lut = np.array(list(info.lut), dtype=np.uint32)
+        for t in range(info.nterms):
+            ok &= ((lut[d[info.t_off[t]:info.t_off[t] + m]] >> (8 * t)) & 1) == 0
+        used.append("lut%d" % info.nterms)
+    return ok, "+".join(used) or "all"
+
+
+@pytest.mark.parametrize("name", G.pattern_names())
+def test_stage1_is_a_superset_of_the_reference_candidates(name):
+    path = G.pattern_path(name)
+    rc, info, pf = describe(path)
+    if rc == 2:
+        pytest.skip("out of scope (rejected at upload)")
+    assert rc == 0
+    op = O.OraclePattern(path)
+    assert info.advance == op.advance
+    total_c = total_p = 0
+    for cname in ("c1", "c2", "c3", "c4", "c5"):
+        data = corpus.block(cname, 60000)
+        cand = op.candidates(data)
+        ok, how = stage1(info, pf, data)
+        m = len(ok)
+        missed = np.flatnonzero(cand[:m] & ~ok)
+        assert missed.size == 0, "%s (%s): stage 1 drops reference candidates at %s of %s" % (name, how, missed[:5], cname)
+        total_c += int(cand[:m].sum())
+        total_p += int(ok.sum())
+    assert total_p >= total_c
+
+
+def test_dfa_export_shapes_of_the_configs():
+    pat = os.path.join(O.ROOT, "ugrep_b200", "patterns")
+    rc, c2, _ = describe(os.path.join(pat, "c2.ugxp"))
+    assert rc == 0 and c2.h4_terms == 3 and c2.max_match_len < 64          # tree DFA of the word list: bounded
+    words = open(os.path.join(pat, "words.txt")).read().split()
+    assert c2.max_match_len == max(len(w) for w in words)
+    rc, c4, _ = describe(os.path.join(pat, "c4.ugxp"))
+    assert rc == 0 and c4.max_match_len == 0xFFFFFFFF and c4.pm2 == 1      # \p{Greek}+ : unbounded
+    rc, c1, _ = describe(os.path.join(pat, "c1.ugxp"))
+    assert rc == 0 and c1.kind == 2 and c1.a_off[0] == 0 and c1.a_chr[0] == ord("S") and c1.max_match_len == 15
+    for info in (c2, c4, c1):
+        assert 1 <= info.first_acc <= info.first_leaf <= info.states
+        assert info.table_bytes == info.states * info.classes * 2

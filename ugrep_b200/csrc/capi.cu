@@ -239,6 +239,48 @@ int ugx_pattern_create(const uint32_t* opc, uint32_t nop, const ugx_prefilter* p
   return UGX_OK;
 }
 
+int ugx_plan_describe(const uint32_t* opc, uint32_t nop, const ugx_prefilter* pf, uint32_t matcher_flags, ugx_plan_info* out)
+{
+  if (opc == nullptr || nop == 0 || pf == nullptr || out == nullptr)
+    return fail(UGX_E_INVALID, "ugx_plan_describe: null argument");
+  ugx::HostDfa dfa;
+  std::string err;
+  int rc = ugx::flatten_dfa(opc, nop, dfa, err);
+  if (rc != UGX_OK)
+    return fail(rc, err);
+  memset(out, 0, sizeof(*out));
+  out->states = dfa.nstates;
+  out->classes = dfa.ncls;
+  out->table_bytes = dfa.table_bytes();
+  out->first_acc = dfa.first_acc;
+  out->first_leaf = dfa.first_leaf;
+  out->max_match_len = dfa.max_match_len;
+  out->has_meta = dfa.has_meta;
+  out->newline_live = dfa.newline_live;
+  const int adv = ugx::select_advance(*pf, matcher_flags);
+  out->advance = adv;
+  ugx::FilterPlan plan;
+  ugx::plan_filter(*pf, adv, plan);
+  out->kind = plan.kind;
+  out->nterms = plan.nterms;
+  for (int i = 0; i < 3; ++i)
+    out->t_off[i] = plan.t_off[i];
+  for (int i = 0; i < 2; ++i)
+  {
+    out->a_off[i] = plan.a_off[i];
+    out->a_chr[i] = plan.a_chr[i] & 0xffu;
+  }
+  out->h4_terms = plan.h4_terms;
+  out->h4_shift = plan.h4_shift;
+  out->pm2 = plan.pm2;
+  out->pm2_shift = plan.pm2_shift;
+  memcpy(out->lut, plan.lut, sizeof(out->lut));
+  rc = ugx::check_scope(dfa, *pf, matcher_flags, err);
+  if (rc != UGX_OK)
+    return fail(rc, err);
+  return UGX_OK;
+}
+
 int ugx_pattern_load(const char* path, int device, ugx_pattern** out)
 {
   FILE* f = fopen(path, "rb");
