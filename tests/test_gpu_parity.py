@@ -310,3 +310,37 @@ def test_misaligned_device_pointers_and_random_slices(gpu):
             rec, _ = sc.find_all(pat, view)
             assert same(rec, op.find_all(data)), (pname, lo, hi)
             assert sc.count_newlines(view).newlines == int((data == 10).sum())
+
+
+def test_full_size_properties(gpu):
+    """BASELINE-sized inputs, checked through size-independent properties: a corpus tiled from R line-aligned copies
+    of one seeded block must give R times the block's counts (the block's counts come from the oracle), and its match
+    records must be the block's records repeated with shifted offsets and line numbers."""
+    import torch
+    api, sc = gpu
+    block_bytes = 32 << 20
+    for pname, cname, mode, gib in (("c1", "c1", "lines", 4), ("c2", "c2", "lines", 2), ("c5", "c5", "matches", 1),
+                                    ("c3b", "c3", "list", 1)):
+        path = os.path.join(PAT_DIR, pname + ".ugxp")
+        pat = api.Pattern.load(path, 0)
+        op = O.OraclePattern(path)
+        block = corpus.block(cname, block_bytes)
+        assert block[-1] == 10
+        reps = (gib << 30) // len(block)
+        dev = torch.from_numpy(block).cuda().repeat(reps)
+        if mode == "lines":
+            assert sc.count_lines(pat, dev).matches == reps * op.count_lines(block), pname
+        elif mode == "matches":
+            assert sc.count_matches(pat, dev).matches == reps * op.count_matches(block), pname
+        else:
+            want = op.find_all(block)
+            tot = sc.find_all_device(pat, dev)
+            assert tot.matches == reps * len(want)
+            nl = int((block == 10).sum())
+            for r in (0, reps // 2, reps - 1):
+                got = sc.fetch(r * len(want), len(want))
+                assert bool(np.all(got["offset"] == want["offset"] + r * len(block))), (pname, r)
+                assert bool(np.all(got["line"] == want["line"] + r * nl)), (pname, r)
+                assert bool(np.all(got["len"] == want["len"])) and bool(np.all(got["cap"] == want["cap"])), (pname, r)
+        del dev
+        torch.cuda.empty_cache()
