@@ -234,10 +234,13 @@ struct Cursor {
   uint32_t cap;
 };
 
-__device__ __forceinline__ void set_current(const Text& t, Cursor& m, uint64_t loc)
+// AbstractMatcher::set_current (absmatcher.h:1576).  `got_` (the byte before the cursor) is only read by the META
+// predicates and by option W: scans without either skip the load (need_got false).
+__device__ __forceinline__ void set_current(const Text& t, Cursor& m, uint64_t loc, bool need_got = true)
 {
   m.pos = m.cur = loc;
-  m.got = loc > 0 ? static_cast<int>(t.raw(loc - 1)) : '\n';
+  if (need_got)
+    m.got = loc > 0 ? static_cast<int>(t.raw(loc - 1)) : '\n';
 }
 
 __device__ __forceinline__ int get_ch(const Text& t, Cursor& m) { return m.pos < t.end ? static_cast<int>(t.raw(m.pos++)) : D_EOF; }

@@ -17,7 +17,7 @@ struct CandMap {
 constexpr int LINE_DONE = 2;
 
 __device__ __forceinline__ bool advance_to(const Text& t, const DevPattern& P, const Tables& T, const CandMap& cm,
-                                           Cursor& m, uint64_t loc, uint64_t last)
+                                           Cursor& m, uint64_t loc, uint64_t last, bool need_got = true)
 {
   // first candidate in [loc, last]; `last` is the line's '\n' (or the final byte of the buffer)
   uint64_t k = loc;
@@ -34,7 +34,7 @@ __device__ __forceinline__ bool advance_to(const Text& t, const DevPattern& P, c
         uint64_t hit = cm.base + (wi << 5) + (__ffs(word) - 1);
         if (hit > last || hit >= t.end)
           return false;
-        set_current(t, m, hit);
+        set_current(t, m, hit, need_got);
         return true;
       }
       if (++wi >= nw)
@@ -49,7 +49,7 @@ __device__ __forceinline__ bool advance_to(const Text& t, const DevPattern& P, c
   {
     if (cand(t, P, T, k))
     {
-      set_current(t, m, k);
+      set_current(t, m, k, need_got);
       return true;
     }
   }
@@ -66,7 +66,8 @@ __device__ __forceinline__ int run_dfa_table(const Text& t, const DevPattern& P,
   uint32_t state = 0;
   for (;;)
   {
-    uint32_t acc = __ldg(P.accept + state);
+    // states 1 .. first_acc - 1 neither accept nor halt (pattern_host.hpp numbering): no table read for them
+    uint32_t acc = (state == 0 || state >= P.first_acc) ? __ldg(P.accept + state) : 0u;
     if ((acc & 0x7fffffffu) != 0 && (!W || at_we(t, P, peek_ch(t, m), m.pos)))
     {
       m.cap = acc & 0x7fffffffu;
@@ -289,10 +290,11 @@ template <bool HAS_META>
 __device__ inline uint32_t find_in_line(const Text& t, const DevPattern& P, const Tables& T, const CandMap& cm, Cursor& m, uint64_t last)
 {
   const bool W = (P.flags & UGX_OPT_W) != 0;
+  const bool G = HAS_META || W; // got_ is needed
   uint32_t retry = 0;
   m.len = 0;
   m.txt = m.cur;
-  if (!advance_to(t, P, T, cm, m, m.cur, last))
+  if (!advance_to(t, P, T, cm, m, m.cur, last, G))
     return 0;
   if (P.lbk > 0)
   {
@@ -306,11 +308,11 @@ __device__ inline uint32_t find_in_line(const Text& t, const DevPattern& P, cons
     {
       m.txt = m.cur;
       m.len = P.len;
-      set_current(t, m, k);
+      set_current(t, m, k, G);
       return m.cap = 1;
     }
   }
-  set_current(t, m, m.cur);
+  set_current(t, m, m.cur, G);
   for (;;)
   {
     m.txt = m.cur;
@@ -324,17 +326,17 @@ __device__ inline uint32_t find_in_line(const Text& t, const DevPattern& P, cons
         if (retry > 0)
         {
           --retry;
-          set_current(t, m, m.cur + 1);
+          set_current(t, m, m.cur + 1, G);
           continue;
         }
         if (m.cur < m.pos)
         {
-          if (!advance_to(t, P, T, cm, m, m.cur + 1, last))
+          if (!advance_to(t, P, T, cm, m, m.cur + 1, last, G))
             return 0;
           if (P.lbk > 0)
           {
             retry = look_back(t, P, m, m.txt + 1);
-            set_current(t, m, m.cur);
+            set_current(t, m, m.cur, G);
             continue;
           }
           if (!P.one)
@@ -345,7 +347,7 @@ __device__ inline uint32_t find_in_line(const Text& t, const DevPattern& P, cons
             continue;
           m.txt = m.cur;
           m.len = P.len;
-          set_current(t, m, k);
+          set_current(t, m, k, G);
           return m.cap = 1;
         }
       }
@@ -359,16 +361,16 @@ __device__ inline uint32_t find_in_line(const Text& t, const DevPattern& P, cons
         return 0;
       if (m.cap != 0)
       {
-        if (!advance_to(t, P, T, cm, m, m.cur + 1, last))
+        if (!advance_to(t, P, T, cm, m, m.cur + 1, last, G))
           return 0;
         continue;
       }
       if (m.cur + 1 > last)
         return 0;
-      set_current(t, m, m.cur + 1);
+      set_current(t, m, m.cur + 1, G);
       continue;
     }
-    set_current(t, m, m.cur);
+    set_current(t, m, m.cur, G);
     return m.cap;
   }
 }
