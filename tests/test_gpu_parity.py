@@ -175,7 +175,7 @@ import golden_lib as G  # noqa: E402
 
 ROUTES = {"default": {}, "generic": {"force_generic": 1}, "legacy_any": {"legacy_any": 1},
           "stream": {"stream_dfa": 1}, "stream_nl": {"stream_dfa": 1, "count_newlines": 1},
-          "two_pass": {"two_pass_records": 1}}
+          "two_pass": {"two_pass_records": 1}, "match_lines": {"match_lines": 1}}
 
 
 @pytest.mark.parametrize("route", list(ROUTES))
@@ -200,7 +200,7 @@ def test_golden_cases(gpu, name, route):
         assert t.matches == case["lines"], (name, route, case["input"], "lines")
         if route == "stream_nl" and t.newlines:
             assert t.newlines == data.count(b"\n"), (name, case["input"], "newlines")
-        if route in ("default", "generic"):
+        if route in ("default", "generic", "match_lines"):
             assert sc.count_matches(pat, data).matches == case["matches"], (name, route, case["input"], "matches")
         if route == "default":
             rec, _ = sc.find_all(pat, data)

@@ -108,6 +108,7 @@ struct ugx_scanner {
   bool force_generic = false; // tests: always take the generic line-scan kernel
   bool legacy_any = false;    // tests / A-B timing: the tile-synchronous count_lines_any kernel instead of the streaming one
   bool count_newlines = false; // the streaming count also counts newlines
+  bool match_lines = false;      // counting takes match_lines_kernel (position-parallel attempts) instead of scan_lines_kernel
   bool two_pass_records = false; // records by count pass + emit pass (A/B against the single-pass staging form)
   uint64_t* tile_base = nullptr;  // staging base of every tile's records
   uint64_t tile_base_cap = 0;
@@ -591,6 +592,26 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
     tt.launches = 1;
     tt.kernel = UGX_K_TILE_ANY;
   }
+  else if (!want_records && !s->force_generic && s->match_lines && ugx::match_lines_eligible(p->dev))
+  {
+    // counting with position-parallel attempts (match_lines.cu); its tiles are smaller than the line scan's
+    const uint64_t tb = ugx::match_lines_tile_bytes(p->dev);
+    const uint64_t nt = (n + tb - 1) / tb;
+    uint64_t c1 = s->tiles_cap, c2 = s->tiles_cap;
+    rc = ensure(s->tile_matches, c1, nt);
+    if (rc == UGX_OK)
+      rc = ensure(s->tile_newlines, c2, nt);
+    s->tiles_cap = c1 < c2 ? c1 : c2;
+    if (rc != UGX_OK)
+      return rc;
+    a.ntiles = nt;
+    a.tile_matches = s->tile_matches;
+    a.tile_newlines = s->tile_newlines;
+    CU(ugx::launch_match_lines(p->dev, a, mode, s->sm_count, s->stream));
+    CU(ugx::launch_tile_prefix(s->tile_matches, s->tile_newlines, nt, s->totals, s->stream));
+    tt.launches = 2;
+    tt.kernel = UGX_K_MATCH_LINES;
+  }
   else if (want_records && !s->two_pass_records)
   {
     // single-pass records: staging pass (tiles in completion order) + prefix + reorder into input order.  The staging
@@ -729,6 +750,7 @@ const char* ugx_kernel_name(uint32_t id)
     case UGX_K_LINE_SCAN: return "scan_lines_kernel";
     case UGX_K_RECORDS: return "scan_records_kernel";
     case UGX_K_NEWLINES: return "count_newlines_kernel";
+    case UGX_K_MATCH_LINES: return "match_lines_kernel";
     default: return "none";
   }
 }
@@ -745,6 +767,11 @@ int ugx_scanner_set_option(ugx_scanner* s, const char* name, int value)
   if (strcmp(name, "legacy_any") == 0)
   {
     s->legacy_any = value != 0;
+    return UGX_OK;
+  }
+  if (strcmp(name, "match_lines") == 0)
+  {
+    s->match_lines = value != 0;
     return UGX_OK;
   }
   if (strcmp(name, "two_pass_records") == 0)

@@ -73,6 +73,11 @@ bool count_lines_literal_eligible(const DevPattern& P);
 cudaError_t launch_count_lines_literal(const DevPattern& P, const uint8_t* buf, uint64_t n, const StreamArgs& a, bool want_nl,
                                        int sm_count, cudaStream_t st);
 
+// find loop with position-parallel attempts (match_lines.cu): counting for patterns without META / W / start-loop skip
+bool match_lines_eligible(const DevPattern& P);
+uint32_t match_lines_tile_bytes(const DevPattern& P);
+cudaError_t launch_match_lines(const DevPattern& P, const ScanArgs& a, int mode, int sm_count, cudaStream_t st);
+
 // single-pass records (records_kernel.cu): staging pass + reorder into input order
 cudaError_t launch_scan_records(const DevPattern& P, const ScanArgs& a, uint64_t* tile_base, ugx_match* stage_out,
                                 uint64_t stage_cap, unsigned long long* cursor, int sm_count, cudaStream_t st);
