@@ -18,7 +18,7 @@
 //   phase D  per line, the sequential rules above on bitmaps and D(): no text access, no DFA.
 //
 // Lines that leave the tile, attempts that run into the end of the buffer and matches longer than 65534 bytes
-// take the line-at-a-time form (find_in_line) instead.
+// take the line-at-a-time form (find_in_line) instead (D() is 8 bits wide: matches of 255 bytes or more too).
 #include "block_scan.cuh"
 #include "device_pattern.cuh"
 #include "line_match.cuh"
@@ -31,7 +31,7 @@ namespace ugx {
 namespace {
 
 constexpr uint32_t ML_STRIP = 32;      // bytes per thread per tile (two 16-byte chunks in phase A)
-constexpr uint16_t ML_FALLBACK = 0xffffu;
+constexpr uint32_t ML_FALLBACK = 0xffu; // D(p) is kept in 8 bits: longer matches take the line-at-a-time form
 
 // first set bit of `bits` at a position in [from, limit] (tile offsets), or 0xffffffff
 __device__ __forceinline__ uint32_t next_set(const uint32_t* bits, uint32_t from, uint32_t limit)
@@ -73,7 +73,7 @@ __device__ __forceinline__ uint32_t run_before(const uint32_t* bits, uint32_t k,
 
 // MODE 0: lines with a match, 1: matches
 template <int MODE, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 2)
+__global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : 3)
 match_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, uint64_t ntiles,
                    uint32_t stage_table, uint64_t* __restrict__ tile_matches, uint64_t* __restrict__ tile_newlines)
 {
@@ -91,8 +91,8 @@ match_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restri
   uint32_t* s_cand = reinterpret_cast<uint32_t*>(s_tap + UGX_BTAP);
   uint32_t* s_nl = s_cand + NW;
   uint32_t* s_cbk = s_nl + NW;
-  uint16_t* s_len = reinterpret_cast<uint16_t*>(s_cbk + NW);       // [TILE] D(p), valid where attempted
-  uint16_t* s_lines = s_len + TILE;                                // [LINE_CAP]
+  uint8_t* s_len = reinterpret_cast<uint8_t*>(s_cbk + NW);         // [TILE] D(p), valid where attempted
+  uint16_t* s_lines = reinterpret_cast<uint16_t*>(s_len + TILE);   // [LINE_CAP]
   uint16_t* s_next = s_lines + LINE_CAP;
   stage_tables_bulk(&s_bar, s_cls, P.cls, s_pred, P.pred, s_tap, P.tap, s_next, P.next,
                     stage_table ? ((P.table_bytes + 15) / 16) * 16 : 0);
@@ -128,9 +128,12 @@ match_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restri
     {
       uint32_t bits = s_cand[threadIdx.x] | s_cbk[threadIdx.x];
       const uint32_t base_off = threadIdx.x * 32;
+      const uint8_t* __restrict__ tb = buf + tile_base;                         // positions are tile-relative, 32 bits
+      const uint64_t left = n - tile_base;
+      const uint32_t lim = left > 0xfffffff0ull ? 0xfffffff0u : static_cast<uint32_t>(left);
+      const uint32_t first_acc = P.first_acc, ncls = P.ncls;
       bool active = false;
-      uint32_t state = 0, off = 0;
-      uint64_t p = 0, acc_at = 0, pos0 = 0;
+      uint32_t state = 0, off = 0, p = 0, acc_at = 0;
       for (;;)
       {
         if (!active)
@@ -140,37 +143,41 @@ match_lines_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restri
           const uint32_t k = __ffs(bits) - 1;
           bits &= bits - 1;
           off = base_off + k;
-          pos0 = tile_base + off;
-          p = pos0;
-          acc_at = pos0;
+          p = off;
+          acc_at = off;
           state = 0;
           active = true;
         }
         bool stop = false, hit_end = false;
-        const uint32_t acc = state >= P.first_acc ? __ldg(P.accept + state) : 0u; // (the start state does not accept)
-        if ((acc & 0x7fffffffu) != 0)
-          acc_at = p;
-        if ((acc & 0x80000000u) != 0)
-          stop = true;
-        else if (p >= n)
+        if (state >= first_acc) // (the start state does not accept: match_lines_eligible)
         {
-          stop = true;
-          hit_end = true;
+          const uint32_t acc = __ldg(P.accept + state);
+          if ((acc & 0x7fffffffu) != 0)
+            acc_at = p;
+          stop = (acc & 0x80000000u) != 0;
         }
-        else
+        if (!stop)
         {
-          const uint32_t ch = __ldg(buf + p);
-          ++p;
-          const uint32_t nxt = T.next[state * P.ncls + T.cls[ch]];
-          if (nxt == D_DEAD)
+          if (p >= lim)
+          {
             stop = true;
+            hit_end = true;
+          }
           else
-            state = nxt;
+          {
+            const uint32_t ch = __ldg(tb + p);
+            ++p;
+            const uint32_t nxt = T.next[state * ncls + T.cls[ch]];
+            if (nxt == D_DEAD)
+              stop = true;
+            else
+              state = nxt;
+          }
         }
         if (stop)
         {
-          const uint64_t len = acc_at - pos0;
-          s_len[off] = (hit_end || len >= ML_FALLBACK) ? ML_FALLBACK : static_cast<uint16_t>(len);
+          const uint32_t len = acc_at - off;
+          s_len[off] = static_cast<uint8_t>((hit_end || len >= ML_FALLBACK) ? ML_FALLBACK : len);
           active = false;
         }
       }
@@ -352,7 +359,7 @@ bool match_lines_eligible(const DevPattern& P)
          P.adv != UGX_ADV_NONE && P.table_bytes <= 150 * 1024;
 }
 
-static int match_lines_threads(const DevPattern& P) { return P.table_bytes > 24 * 1024 ? 1024 : 256; }
+static int match_lines_threads(const DevPattern& P) { return P.table_bytes > 24 * 1024 ? 512 : 256; }
 
 uint32_t match_lines_tile_bytes(const DevPattern& P) { return static_cast<uint32_t>(match_lines_threads(P)) * ML_STRIP; }
 
@@ -360,7 +367,7 @@ template <int MODE, int THREADS>
 static cudaError_t launch_ml(const DevPattern& P, const ScanArgs& a, int sm_count, cudaStream_t st)
 {
   constexpr uint32_t TILE = THREADS * ML_STRIP;
-  const size_t smem = 256 + UGX_HASH + UGX_BTAP + 3 * (TILE / 8) + 2 * TILE + 2 * (THREADS * 2) +
+  const size_t smem = 256 + UGX_HASH + UGX_BTAP + 3 * (TILE / 8) + TILE + 2 * (THREADS * 2) +
                       ((P.table_bytes + 15) / 16) * 16;
   auto kern = match_lines_kernel<MODE, THREADS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -383,8 +390,8 @@ static cudaError_t launch_ml(const DevPattern& P, const ScanArgs& a, int sm_coun
 
 cudaError_t launch_match_lines(const DevPattern& P, const ScanArgs& a, int mode, int sm_count, cudaStream_t st)
 {
-  if (match_lines_threads(P) == 1024)
-    return mode == 0 ? launch_ml<0, 1024>(P, a, sm_count, st) : launch_ml<1, 1024>(P, a, sm_count, st);
+  if (match_lines_threads(P) == 512)
+    return mode == 0 ? launch_ml<0, 512>(P, a, sm_count, st) : launch_ml<1, 512>(P, a, sm_count, st);
   return mode == 0 ? launch_ml<0, 256>(P, a, sm_count, st) : launch_ml<1, 256>(P, a, sm_count, st);
 }
 
