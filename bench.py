@@ -106,6 +106,22 @@ def measured_traffic(cfg: str, kernel: str, nbytes: int):
     return None
 
 
+def measured_smem(cfg: str, kernel: str, nbytes: int):
+    """shared-memory lookup pressure of the dominant kernel from the same capture: LSU shared wavefronts per cycle per
+    SM (peak 1.0 = 128 B/clk/SM) and the share of them that are bank-conflict replays"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(cfg)
+        if t and t["kernel"] == kernel and t["nbytes"] == nbytes and "smem_wavefronts_per_launch" in t:
+            wf = t["smem_wavefronts_per_launch"]
+            return {"wavefronts_per_clk_per_sm": round(wf / 148.0 / t["sm_cycles_per_launch"], 3), "peak": 1.0,
+                    "bank_conflict_share": round(t["smem_bank_conflict_wavefronts_per_launch"] / wf, 3),
+                    "lookups_per_byte": round(wf * 32.0 / nbytes, 2), "source": t["source"]}
+    except Exception:
+        pass
+    return None
+
+
 def make_block(cfg: str):
     from ugrep_b200 import corpus
     return corpus.block(CONFIGS[cfg][1], BLOCK_BYTES)
@@ -376,7 +392,7 @@ def main():
             "hbm_frac": round(value / world / peak, 4),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": measured_traffic(cfg, tot.kernel, nbytes),
-                         "algorithmic_bytes": nbytes, "peak_kind": peak_kind,
+                         "algorithmic_bytes": nbytes, "smem": measured_smem(cfg, tot.kernel, nbytes), "peak_kind": peak_kind,
                          "kernel": tot.kernel, "kernel_ms": round(k_ms, 4)},
             "cpu_baseline": cpu,
             "e2e": e2e,
