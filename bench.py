@@ -116,7 +116,7 @@ def measured_smem(cfg: str, kernel: str, nbytes: int):
             wf = t["smem_wavefronts_per_launch"]
             return {"wavefronts_per_clk_per_sm": round(wf / 148.0 / t["sm_cycles_per_launch"], 3), "peak": 1.0,
                     "bank_conflict_share": round(t["smem_bank_conflict_wavefronts_per_launch"] / wf, 3),
-                    "lookups_per_byte": round(wf * 32.0 / nbytes, 2), "source": t["source"]}
+                    "wavefronts_per_kib": round(wf * 1024.0 / nbytes, 1), "source": t["source"]}
     except Exception:
         pass
     return None
