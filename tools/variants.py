@@ -3,6 +3,9 @@
 
     python tools/variants.py stream_count.cu v_spans2:-DUGX_SC_SPANS=2 v_minb4:-DUGX_SC_MINB=4 ...
 
+NOTE: only macros that are private to that one source may be varied.  A macro shared through a header (for example
+UGX_SC_REGION, which capi.cu and stream_count.cu read too) gives an inconsistent library — that hung a kernel once.
+
 Each variant becomes ugrep_b200/build/<name>.so (all other objects are shared with the main build);
 select one at run time with UGX_LIB=ugrep_b200/build/<name>.so.
 """

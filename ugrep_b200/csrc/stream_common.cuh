@@ -411,6 +411,8 @@ __device__ __forceinline__ void stream_scan(const uint8_t* __restrict__ buf, uin
   while (r < nregions)
   {
     const uint64_t rbase = r * SC_REGION;
+    if (rbase >= n)
+      break; // defensive: a region range that does not match the valid bytes must not spin
     const uint64_t rnext = a.region_begin + sched.next(lane);
     const bool have_next = rnext < nregions;
     const uint64_t next_rbase = rnext * SC_REGION;
