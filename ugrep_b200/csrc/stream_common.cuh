@@ -319,6 +319,8 @@ __device__ __forceinline__ void stream_region(const uint8_t* __restrict__ buf, u
   const uint64_t rend = FULL ? rbase + SC_REGION : (rbase + SC_REGION < n ? rbase + SC_REGION : n);
   const uint32_t nblocks = FULL ? SC_REGION / SC_BLOCK : static_cast<uint32_t>((rend - rbase + SC_BLOCK - 1) / SC_BLOCK);
   const uint8_t* __restrict__ p = buf + rbase + lane * 16; // this lane's chunk 0 of the current block
+  const uint8_t* pnr = buf + next_rbase + lane * 16;        // ... and of the first block of the warp's next region
+  asm volatile("" : "+l"(pnr));                              // (kept in registers: not recomputed per block)
   uint32_t nlacc = 0;                                      // WANT_NL: per-byte-lane newline counters, flushed per block
   for (uint32_t b = 0; b < nblocks; ++b)
   {
@@ -326,7 +328,7 @@ __device__ __forceinline__ void stream_region(const uint8_t* __restrict__ buf, u
     const bool last = b + 1 == nblocks;
     const bool has_next = !last || have_next;
     const uint64_t nbase = last ? next_rbase : bbase + SC_BLOCK;
-    const uint8_t* pn = last ? buf + next_rbase + lane * 16 : p + SC_BLOCK;
+    const uint8_t* pn = last ? pnr : p + SC_BLOCK;
     asm volatile("" : "+l"(pn)); // keep the reload pointer in registers: ptxas otherwise recomputes it for every span
     const bool next_full = FULL || nbase + SC_BLOCK + 16 <= n;
     if (FULL && UGX_SC_PF > 0 && lane == 0)
