@@ -74,9 +74,12 @@ class OraclePattern:
             raise RuntimeError("ora_pattern_load(%s) -> %d" % (path, rc))
 
     def __del__(self):
-        if getattr(self, "handle", None):
-            lib().ora_pattern_destroy(self.handle)
-            self.handle = None
+        try:
+            if getattr(self, "handle", None):
+                lib().ora_pattern_destroy(self.handle)
+                self.handle = None
+        except Exception:  # interpreter shutdown: module globals may be gone already
+            pass
 
     @property
     def advance(self) -> int:
