@@ -23,13 +23,16 @@ def main():
     ap.add_argument("--gib", type=float, default=1.0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--generic", action="store_true")
+    ap.add_argument("--pattern", default=None, help="a .ugxp file instead of the config's pattern")
+    ap.add_argument("--mode", default=None, choices=["lines", "matches", "list"])
     ap.add_argument("--opt", action="append", default=[], help="scanner option name=value")
     a = ap.parse_args()
     pname, cname, mode = CFG[a.config]
     block = corpus.block(cname, 64 << 20)
     reps = max(1, int(a.gib * (1 << 30)) // block.size)
     dev = torch.from_numpy(block).cuda().repeat(reps)
-    pat = api.Pattern.load(os.path.join(ROOT, "ugrep_b200", "patterns", pname + ".ugxp"), 0)
+    pat = api.Pattern.load(a.pattern or os.path.join(ROOT, "ugrep_b200", "patterns", pname + ".ugxp"), 0)
+    mode = a.mode or mode
     sc = api.Scanner(0, torch.cuda.current_stream().cuda_stream)
     if a.generic:
         sc.set_option("force_generic", 1)

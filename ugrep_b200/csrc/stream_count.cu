@@ -384,7 +384,10 @@ struct DfaEval {
 } // namespace
 
 template <int KIND, bool WANT_NL, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : 2)
+#ifndef UGX_DFA_MINB
+#define UGX_DFA_MINB 3
+#endif
+__global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : UGX_DFA_MINB)
 count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, StreamArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem[];
