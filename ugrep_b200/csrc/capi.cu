@@ -491,7 +491,8 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
   uint64_t h2d = 0;
   const bool stream_route = mode == 0 && !want_records && !s->force_generic && !s->legacy_any &&
                             ugx::count_lines_stream_eligible(p->dev) &&
-                            (s->stream_dfa || ugx::count_lines_literal_eligible(p->dev) || p->dev.plan.h4_terms >= 1 || p->dev.plan.pm2 != 0);
+                            (s->stream_dfa || ugx::count_lines_literal_eligible(p->dev) || p->dev.plan.h4_terms >= 1 || p->dev.plan.pm2 != 0 ||
+                             (p->dev.plan.kind == ugx::FK_LUT && p->dev.plan.nterms >= 1 && p->dev.one == 0));
   // a host buffer on the streaming route is copied chunk by chunk, overlapped with the scan, when every read of a
   // scanned position stays within one region of it: pure literals, and DFAs whose longest match is bounded
   const bool bounded = ugx::count_lines_literal_eligible(p->dev) || p->dfa.max_match_len < ugx::SC_REGION - 512;
