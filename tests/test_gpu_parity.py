@@ -344,3 +344,34 @@ def test_full_size_properties(gpu):
                 assert bool(np.all(got["len"] == want["len"])) and bool(np.all(got["cap"] == want["cap"])), (pname, r)
         del dev
         torch.cuda.empty_cache()
+
+
+def test_scanners_on_two_host_threads_share_a_pattern(gpu):
+    """a ugx_pattern is shareable, a ugx_scanner belongs to one host thread: two threads scanning at once with
+    different patterns (different table sizes, hence different shared-memory needs of the same kernels)"""
+    import threading
+    api, _ = gpu
+    jobs = []
+    for pname, cname in (("c2", "c2"), ("c5", "c5"), ("c4", "c4"), ("c3b", "c3")):
+        path = os.path.join(PAT_DIR, pname + ".ugxp")
+        data = corpus.block(cname, 2 << 20)
+        op = O.OraclePattern(path)
+        jobs.append((api.Pattern.load(path, 0), data, op.count_lines(data), op.count_matches(data)))
+    errors = []
+
+    def worker(seed):
+        try:
+            sc = api.Scanner(0)
+            for i in range(12):
+                pat, data, want_l, want_m = jobs[(seed + i) % len(jobs)]
+                if sc.count_lines(pat, data).matches != want_l or sc.count_matches(pat, data).matches != want_m:
+                    errors.append((seed, i))
+        except Exception as ex:  # noqa: BLE001
+            errors.append((seed, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors

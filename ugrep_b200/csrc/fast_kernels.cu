@@ -329,7 +329,7 @@ cudaError_t launch_count_lines_any(const DevPattern& P, const uint8_t* buf, uint
                                    int sm_count, cudaStream_t st)
 {
   const uint64_t ntiles = (n + ANY_TILE - 1) / ANY_TILE;
-  const bool stage = P.has_meta == 0 && any_smem_bytes(P, true) <= 227 * 1024 - 1024;
+  const bool stage = P.has_meta == 0 && any_smem_bytes(P, true) <= static_cast<size_t>(UGX_MAX_DYN_SMEM);
   const size_t smem = any_smem_bytes(P, stage);
   // big tables leave room for one CTA per SM: make it a full 1024-thread CTA; otherwise 512-thread CTAs
   const int threads = (!P.has_meta && smem > 100 * 1024) ? 1024 : 512;
@@ -351,7 +351,7 @@ cudaError_t launch_count_lines_any(const DevPattern& P, const uint8_t* buf, uint
   do                                                                                                                      \
   {                                                                                                                       \
     e = cudaFuncSetAttribute(count_lines_any_kernel<META, THR>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                             static_cast<int>(smem));                                                                     \
+                             UGX_MAX_DYN_SMEM);                                                                     \
     if (e != cudaSuccess)                                                                                                 \
       return e;                                                                                                           \
     count_lines_any_kernel<META, THR><<<static_cast<int>(g), THR, smem, st>>>(P, buf, n, ntiles, st_flag, totals);         \

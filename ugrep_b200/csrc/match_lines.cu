@@ -370,7 +370,7 @@ static cudaError_t launch_ml(const DevPattern& P, const ScanArgs& a, int sm_coun
   const size_t smem = 256 + UGX_HASH + UGX_BTAP + 3 * (TILE / 8) + TILE + 2 * (THREADS * 2) +
                       ((P.table_bytes + 15) / 16) * 16;
   auto kern = match_lines_kernel<MODE, THREADS>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, UGX_MAX_DYN_SMEM);
   if (e != cudaSuccess)
     return e;
   int per_sm = 1;

@@ -216,7 +216,7 @@ static cudaError_t launch_records_one(const DevPattern& P, const ScanArgs& a, bo
                                       unsigned long long* cursor, cudaStream_t st)
 {
   auto kern = scan_records_kernel<HAS_META, THREADS>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, UGX_MAX_DYN_SMEM);
   if (e != cudaSuccess)
     return e;
   kern<<<grid, THREADS, smem, st>>>(P, a.buf, a.n, a.ntiles, stage ? 1u : 0u, a.tile_matches, a.tile_newlines, tile_base,
@@ -229,7 +229,7 @@ cudaError_t launch_scan_records(const DevPattern& P, const ScanArgs& a, uint64_t
 {
   const int threads = scan_threads(P); // the tile size must agree with scan_tile_bytes(): the caller sized ntiles by it
   const bool stage = P.has_meta == 0 && P.table_bytes <= SCAN_MAX_SMEM_TABLE &&
-                     records_smem_bytes(P, true, threads) <= 227 * 1024 - 2048;
+                     records_smem_bytes(P, true, threads) <= static_cast<size_t>(UGX_MAX_DYN_SMEM);
   const size_t smem = records_smem_bytes(P, stage, threads);
   int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
   if (per_sm > 2048 / threads)

@@ -304,7 +304,7 @@ template <int MODE, bool EMIT, bool HAS_META, int THREADS>
 static cudaError_t launch_one(const DevPattern& P, const ScanArgs& a, bool stage, int grid, size_t smem, cudaStream_t st)
 {
   auto kern = scan_lines_kernel<MODE, EMIT, HAS_META, THREADS>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, UGX_MAX_DYN_SMEM);
   if (e != cudaSuccess)
     return e;
   kern<<<grid, THREADS, smem, st>>>(P, a.buf, a.n, a.ntiles, stage ? 1u : 0u, a.tile_matches, a.tile_newlines,
@@ -314,8 +314,9 @@ static cudaError_t launch_one(const DevPattern& P, const ScanArgs& a, bool stage
 
 cudaError_t launch_scan_lines(const DevPattern& P, const ScanArgs& a, int mode, bool emit, int sm_count, cudaStream_t st)
 {
-  const bool stage = P.has_meta == 0 && P.table_bytes <= SCAN_MAX_SMEM_TABLE;
   const int threads = scan_threads(P);
+  const bool stage = P.has_meta == 0 && P.table_bytes <= SCAN_MAX_SMEM_TABLE &&
+                     scan_smem_bytes(P, true, threads) <= static_cast<size_t>(UGX_MAX_DYN_SMEM);
   const size_t smem = scan_smem_bytes(P, stage, threads);
   // persistent grid: as many CTAs as fit per SM, times the SM count, capped by the number of tiles
   int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));

@@ -11,6 +11,10 @@ namespace ugx {
 struct DevPattern;
 
 constexpr int SCAN_THREADS = 256;                      // threads per CTA (512 for big staged tables: scan_threads())
+// Dynamic shared memory every kernel opts in to (the 227 KiB per-CTA limit minus room for static shared memory).  The
+// attribute is set to this one value for every pattern: it is process-global per kernel, and scanners on different
+// host threads may launch the same kernel with different tables.
+constexpr int UGX_MAX_DYN_SMEM = 227 * 1024 - 4096;
 constexpr int SCAN_STRIP = 64;                         // bytes per thread per tile
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_STRIP;   // bytes per CTA iteration (16 KiB)
 constexpr uint32_t SCAN_LINE_CAP = 1024;                // line starts per tile the dense line list holds

@@ -472,7 +472,7 @@ static cudaError_t launch_dfa(const DevPattern& P, const uint8_t* buf, uint64_t 
                               int sm_count, cudaStream_t st)
 {
   auto kern = count_lines_stream_kernel<KIND, WANT_NL, THREADS>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, UGX_MAX_DYN_SMEM);
   if (e != cudaSuccess)
     return e;
   int per_sm = 1;
@@ -489,7 +489,7 @@ cudaError_t launch_count_lines_stream(const DevPattern& P, const uint8_t* buf, u
   if (count_lines_literal_eligible(P))
     return launch_count_lines_literal(P, buf, n, a, want_nl, sm_count, st);
   const bool meta = P.has_meta != 0;
-  const bool stage = !meta && stream_smem_bytes(P, true, 1024) <= 227 * 1024 - 1024;
+  const bool stage = !meta && stream_smem_bytes(P, true, 1024) <= static_cast<size_t>(UGX_MAX_DYN_SMEM);
   // a big staged table leaves room for one CTA per SM: make it a full 1024-thread CTA
   const bool big = stage && stream_smem_bytes(P, true, 256) > 100 * 1024;
   const size_t smem = stream_smem_bytes(P, stage, big ? 1024 : 256);
