@@ -38,6 +38,7 @@ GIB = 1 << 30
 CONFIGS = {
     "c1": ("c1", "c1", "lines", ["-c", "-F", "Sherlock Holmes"], 1),
     "c2": ("c2", "c2", "lines", ["-c", "-F", "-f", "@WORDS@"], 4),
+    "c3": ("c3", "c3", "list", ["-n", "-b", "-o", "[A-Z][a-z]+ing\\b"], 4),
     "c3b": ("c3b", "c3", "list", ["-n", "-b", "-o", "[A-Z][a-z]+ing"], 4),
     "c4": ("c4", "c4", "lines", ["-i", "-c", "\\p{Greek}+|naïve\\w*"], 8),
     "c5": ("c5", "c5", "matches", ["-c", "-o", "-e", "ERROR|WARN", "-e", "\\d{3}-\\d{4}"], 8),
@@ -45,6 +46,7 @@ CONFIGS = {
 WORKLOAD_TEXT = {
     "c1": "ugrep -c -F 'Sherlock Holmes' over synthetic ASCII text",
     "c2": "ugrep -c -F -f words.txt (1,000-literal alternation) over synthetic text",
+    "c3": "ugrep -n -b -o '[A-Z][a-z]+ing\\b' (config 3 as named: the reference's prefilter admits no candidate, empty output) over synthetic text",
     "c3b": "ugrep -n -b -o '[A-Z][a-z]+ing' (match records) over synthetic text",
     "c4": "ugrep -i -c '\\p{Greek}+|naïve\\w*' over mixed UTF-8",
     "c5": "ugrep -c -o -e 'ERROR|WARN' -e '\\d{3}-\\d{4}' over a synthetic log corpus",

@@ -77,6 +77,7 @@ struct ugx_pattern {
   ugx_prefilter pf;
   uint32_t flags = 0;
   int adv = 0;
+  bool never = false; // the prefilter tables admit no candidate at all (config 3): every scan finds nothing
   int device = 0;
   uint32_t nop = 0;
   ugx::DevPattern dev;
@@ -151,6 +152,7 @@ int ugx_pattern_create(const uint32_t* opc, uint32_t nop, const ugx_prefilter* p
   p->pf = *pf;
   p->flags = matcher_flags;
   p->adv = ugx::select_advance(*pf, matcher_flags);
+  p->never = ugx::prefilter_never_fires(*pf, p->adv);
   p->device = device;
   p->nop = nop;
   cudaError_t ce = cudaSetDevice(device);
@@ -508,6 +510,25 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
     rc = resolve(s, buf, n, &dbuf, &h2d);
   if (rc != UGX_OK)
     return rc;
+  if (p->never)
+  {
+    // no position can be a candidate: the result is empty; the pass over the text only counts newlines
+    CU(cudaEventRecord(s->ev0, s->stream));
+    CU(ugx::launch_count_newlines(dbuf, n, s->totals + 1, s->sm_count, s->stream));
+    CU(cudaMemcpyAsync(s->h_totals + 1, s->totals + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaEventRecord(s->ev1, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    float ms0 = 0;
+    CU(cudaEventElapsedTime(&ms0, s->ev0, s->ev1));
+    tt.newlines = s->h_totals[1];
+    tt.kernel_ms = ms0;
+    tt.launches = 1;
+    tt.kernel = UGX_K_NEWLINES;
+    s->records_n = 0;
+    if (totals)
+      *totals = tt;
+    return UGX_OK;
+  }
   const uint64_t tile_bytes = ugx::scan_tile_bytes(p->dev);
   const uint64_t ntiles = (n + tile_bytes - 1) / tile_bytes;
   const uint64_t nstrips = (n + ugx::SCAN_STRIP - 1) / ugx::SCAN_STRIP;

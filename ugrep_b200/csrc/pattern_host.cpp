@@ -410,6 +410,23 @@ double add_term(FilterPlan& plan, uint32_t off, const bool (&in_set)[256])
 
 } // namespace
 
+bool prefilter_never_fires(const ugx_prefilter& pf, int adv)
+{
+  if (adv != UGX_ADV_MIN1 && adv != UGX_ADV_MIN2 && adv != UGX_ADV_MIN3 && adv != UGX_ADV_MIN4)
+    return false;
+  // every one of these routines requires bit j of tap[pair(k + j)] to be clear for all j < depth (MIN1: j = 0)
+  const uint32_t depth = pf.min < 1 ? 1 : pf.min;
+  for (uint32_t j = 0; j < depth && j < 8; ++j)
+  {
+    bool some = false;
+    for (uint32_t i = 0; i < UGX_BTAP && !some; ++i)
+      some = ((pf.tap[i] >> j) & 1u) == 0;
+    if (!some)
+      return true;
+  }
+  return false;
+}
+
 void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan)
 {
   memset(&plan, 0, sizeof(plan));

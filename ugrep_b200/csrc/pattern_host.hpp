@@ -51,6 +51,10 @@ int select_advance(const ugx_prefilter& pf, uint32_t matcher_flags);
 // returns UGX_OK or an error status; err receives a message
 int flatten_dfa(const uint32_t* opc, uint32_t nop, HostDfa& out, std::string& err);
 
+// true when the routine's tables admit no candidate position at all: a bitap step j < min_ that no byte pair passes
+// (the advance_pattern_min* routines, lib/matcher.cpp:2235-2660, then never stop — config 3)
+bool prefilter_never_fires(const ugx_prefilter& pf, int adv);
+
 // first-stage filter of the position-parallel kernels (filter_plan.hpp)
 void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan);
 
