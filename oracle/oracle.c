@@ -7,9 +7,10 @@
  *
  * Scope of the restatement (same as the product): in-place one-pass buffers
  * (AbstractMatcher::buffer, include/reflex/absmatcher.h:542-591), method FIND,
- * patterns without HEAD/TAIL/REDO opcodes, matcher option W honoured; option N
- * (ugrep -Y, implied by ^... and ...$ patterns, src/cnf.hpp:199-203) honoured for
- * patterns that cannot match the empty string.
+ * patterns without HEAD/TAIL/REDO opcodes, matcher options W and N honoured
+ * (N = ugrep -Y, implied by ^... and ...$ patterns, src/cnf.hpp:199-203: find()
+ * then returns empty matches, lib/matcher.cpp:681-728, and a pattern whose
+ * minimum length is 0 is searched without a prefilter, :804).
  *
  * The prefilters are restated in POSITION-LOCAL form: cand(k) says whether the
  * reference's advance routine can stop at byte k.  Where the reference's SIMD
@@ -680,9 +681,14 @@ scan:
       set_current(m, m->cur);
       return m->cap = 0;
     }
-    if (m->cap != 0) /* an empty match: discarded without option N, :692-714 (with N: patterns that can match empty are out of scope) */
+    if (m->cap != 0) /* an empty match, :692-721 */
     {
-      if (advance(m, m->cur + 1))
+      if (p->flags & UGX_OPT_N) /* option N: accepted; the next find() starts one byte on */
+      {
+        set_current(m, m->cur + 1);
+        return m->cap;
+      }
+      if (advance(m, m->cur + 1)) /* discarded: keep looking for a non-empty match */
         goto scan;
       return m->cap = 0;
     }
@@ -711,39 +717,6 @@ static int check_opcodes(const uint32_t *opc, uint32_t nop)
   return UGX_OK;
 }
 
-/* can the pattern match the empty string?  (a TAKE reachable from the start state through META edges alone) */
-static int nullable(const uint32_t *opc, uint32_t nop)
-{
-  uint32_t stack[64], seen[64];
-  int sp = 0, ns = 0;
-  stack[sp++] = 0;
-  while (sp > 0)
-  {
-    uint32_t pc = stack[--sp];
-    int dup = 0;
-    for (int i = 0; i < ns; ++i)
-      dup |= seen[i] == pc;
-    if (dup || ns >= 64)
-      continue;
-    seen[ns++] = pc;
-    for (; pc < nop && !op_is_goto(opc[pc]); ++pc)
-    {
-      unsigned code = opc[pc] >> 24;
-      if (code == 0xfe)
-        return 1;
-      if (code >= 0x01 && code <= 0x0c) /* META edge */
-      {
-        uint32_t t = opc[pc] & 0xffff;
-        if (t == IDX_LONG && pc + 1 < nop)
-          t = opc[++pc] & 0xffffff;
-        if (t < nop && sp < 64)
-          stack[sp++] = t;
-      }
-    }
-  }
-  return 0;
-}
-
 int ora_pattern_create(const uint32_t *opc, uint32_t nop, const ugx_prefilter *pf, uint32_t matcher_flags, ora_pattern **out)
 {
   if (opc == NULL || nop == 0 || pf == NULL || out == NULL)
@@ -751,8 +724,6 @@ int ora_pattern_create(const uint32_t *opc, uint32_t nop, const ugx_prefilter *p
   int rc = check_opcodes(opc, nop);
   if (rc != UGX_OK)
     return rc;
-  if ((matcher_flags & UGX_OPT_N) && nullable(opc, nop)) /* accepted empty matches (ugrep -Y): out of scope */
-    return UGX_E_UNSUPPORTED;
   ora_pattern *p = calloc(1, sizeof(*p));
   if (p == NULL)
     return UGX_E_NOMEM;

@@ -209,7 +209,8 @@ static int do_dump(const POpts& o, const std::string& out)
   memcpy(pf.tap, pattern.tap_, sizeof(pf.tap));
   memcpy(pf.pma, pattern.pma_, sizeof(pf.pma));
   memcpy(pf.pmh, pattern.pmh_, sizeof(pf.pmh));
-  memcpy(pf.bms, pattern.bms_, 256);
+  if (pattern.bmd_ > 0) // bms_ is only written (and read) for the Boyer-Moore routines; left zero otherwise so that dumps are deterministic
+    memcpy(pf.bms, pattern.bms_, 256);
   for (int c = 0; c < 256; ++c)
   {
     if (pattern.cbk_.test(c))

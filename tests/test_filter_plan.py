@@ -103,7 +103,7 @@ def test_stage1_is_a_superset_of_the_reference_candidates(name):
 def test_dfa_export_shapes_of_the_configs():
     pat = os.path.join(O.ROOT, "ugrep_b200", "patterns")
     rc, c2, _ = describe(os.path.join(pat, "c2.ugxp"))
-    assert rc == 0 and c2.h4_terms == 3 and c2.max_match_len < 64          # tree DFA of the word list: bounded
+    assert rc == 0 and c2.h4_terms == 1 and c2.max_match_len < 64          # tree DFA of the word list: bounded
     words = open(os.path.join(pat, "words.txt")).read().split()
     assert c2.max_match_len == max(len(w) for w in words)
     rc, c4, _ = describe(os.path.join(pat, "c4.ugxp"))

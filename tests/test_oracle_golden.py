@@ -39,8 +39,10 @@ def test_golden_covers_every_prefilter_family():
              8: "min2", 9: "min3", 10: "min4", 11: "pma", 12: "char", 13: "char_pma", 14: "char_pmh", 15: "string",
              16: "string_pma", 17: "string_pmh"}
     missing = sorted(names[k] for k in names if k not in seen)
-    # families with no pattern in the suite must be listed here on purpose
-    assert set(missing) <= {"char_pma", "char_pmh", "min3"}, missing
+    # char_pma / char_pmh (len_ == 1 with min_ > 0) cannot be produced by the reference's compiler in SIMD builds: a
+    # one-byte literal prefix is kept only when the state after it accepts, and then nothing follows for the predictor
+    # (min_ = 0, advance_char); otherwise len_ is reset to 0 (lib/pattern.cpp:4328-4334).  Every other family is covered.
+    assert set(missing) == {"char_pma", "char_pmh"}, missing
 
 
 SGR = re.compile(rb"\x1b\[[0-9;]*m")

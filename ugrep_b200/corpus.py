@@ -112,33 +112,48 @@ _SYLL = ("ba be bi bo bu da de di do du fa fe fi fo fu ga ge gi go gu ka ke ki k
          "ma me mi mo mu na ne ni no nu ra re ri ro ru sa se si so su ta te ti to tu").split()
 
 
-def _syllable_words(rng: np.random.Generator, count: int, lo: int, hi: int, taken: set[bytes]) -> list[bytes]:
+def _syllable_words(rng: np.random.Generator, count: int, lo: int, hi: int, taken: set[bytes],
+                    avoid: set[bytes] | None = None) -> list[bytes]:
+    """``count`` distinct words of lo..hi syllables that are not in ``taken``; with ``avoid``, words that contain one of
+    those (syllable strings) anywhere are skipped as well."""
     out: list[bytes] = []
     while len(out) < count:
         n = int(rng.integers(lo, hi + 1))
         w = "".join(_SYLL[int(i)] for i in rng.integers(0, len(_SYLL), size=n)).encode()
-        if w not in taken:
-            taken.add(w)
-            out.append(w)
+        if w in taken:
+            continue
+        if avoid is not None and any(w[2 * i:2 * j] in avoid for i in range(n) for j in range(i + 1, n + 1)):
+            continue
+        taken.add(w)
+        out.append(w)
     return out
 
 
 def words_list(seed: int = 11, count: int = 1000) -> list[bytes]:
-    """c2 words.txt: ``count`` distinct lowercase words of 3-5 syllables, sorted."""
+    """c2 words.txt: ``count`` distinct lowercase words of 2-5 syllables from a 50-syllable table, sorted
+    (SURVEY.md 8(d)-2)."""
     rng = np.random.default_rng(seed)
-    return sorted(_syllable_words(rng, count, 3, 5, set()))
+    return sorted(_syllable_words(rng, count, 2, 5, set()))
 
 
-def needles(nbytes: int, seed: int = 11, p_needle: float = 0.004, count: int = 1000) -> np.ndarray:
-    """c2 text: lines of 2-12 words; a word is one of the ``count`` needles with probability
-    ``p_needle``, else one of 20 000 distractors (2-3 syllable words plus a digit, so that a
-    distractor never contains a needle)."""
+def needles(nbytes: int, seed: int = 11, p_needle: float = 0.004, count: int = 1000, dense: bool = False) -> np.ndarray:
+    """c2 text: lines of 2-12 words.
+
+    ``dense`` (the headline corpus): words drawn uniformly from the ``count`` needles and 20 000
+    distractors made the same way as the needles (2-5 syllables, no marker), so a needle may also occur inside a
+    longer distractor and most word starts look like needle starts to the prefilter.
+    sparse (``c2s``): a word is a needle with probability ``p_needle``, else one of 20 000 distractors of 2-3
+    syllables plus a digit, so that a distractor never contains a needle (<= 3 % matching lines)."""
     rng = np.random.default_rng(seed)
     needle_words = words_list(seed, count)
     rng2 = np.random.default_rng(seed + 1)
     taken = set(needle_words)
-    base = _syllable_words(rng2, 20000, 2, 3, taken)
-    distract = [w + str(int(d)).encode() for w, d in zip(base, rng2.integers(0, 10, size=len(base)))]
+    if dense:
+        distract = _syllable_words(rng2, 20000, 2, 5, taken)
+        p_needle = count / float(count + len(distract))
+    else:
+        base = _syllable_words(rng2, 20000, 2, 3, taken, avoid=set(needle_words))
+        distract = [w + str(int(d)).encode() for w, d in zip(base, rng2.integers(0, 10, size=len(base)))]
     words = distract + needle_words
     nw = len(words)
     vocab = _variants(words, False, b"")
@@ -223,10 +238,12 @@ def logs(nbytes: int, seed: int = 7) -> np.ndarray:
 
 
 def block(config: str, nbytes: int, seed: int | None = None) -> np.ndarray:
-    """A line-aligned block of about ``nbytes`` for config c1..c5."""
+    """A line-aligned block of about ``nbytes`` for config c1..c5 (c2 = the dense variant, c2s = the sparse one)."""
     if config == "c1":
         return english(nbytes, 42 if seed is None else seed)
     if config == "c2":
+        return needles(nbytes, 11 if seed is None else seed, dense=True)
+    if config == "c2s":
         return needles(nbytes, 11 if seed is None else seed)
     if config == "c3":
         return ing(nbytes, 42 if seed is None else seed)

@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -132,12 +134,34 @@ extern "C" {
 const char* ugx_last_error(void) { return g_err.c_str(); }
 int ugx_abi_version(void) { return UGX_ABI_VERSION; }
 
+static int pattern_create_impl(const uint32_t* opc, uint32_t nop, const ugx_prefilter* pf, uint32_t matcher_flags, int device,
+                               ugx_pattern** out);
+
+// no C++ exception may cross the C ABI: allocation failures inside the export become status codes
 int ugx_pattern_create(const uint32_t* opc, uint32_t nop, const ugx_prefilter* pf, uint32_t matcher_flags, int device,
                        ugx_pattern** out)
 {
+  try
+  {
+    return pattern_create_impl(opc, nop, pf, matcher_flags, device, out);
+  }
+  catch (const std::bad_alloc&)
+  {
+    return fail(UGX_E_NOMEM, "out of host memory");
+  }
+  catch (const std::exception& ex)
+  {
+    return fail(UGX_E_INVALID, std::string("ugx_pattern_create: ") + ex.what());
+  }
+}
+
+static int pattern_create_impl(const uint32_t* opc, uint32_t nop, const ugx_prefilter* pf, uint32_t matcher_flags, int device,
+                               ugx_pattern** out)
+{
   if (opc == nullptr || nop == 0 || pf == nullptr || out == nullptr)
     return fail(UGX_E_INVALID, "ugx_pattern_create: null argument");
-  ugx_pattern* p = new (std::nothrow) ugx_pattern();
+  std::unique_ptr<ugx_pattern> holder(new (std::nothrow) ugx_pattern()); // freed on every early return and on a throw
+  ugx_pattern* p = holder.get();
   if (p == nullptr)
     return fail(UGX_E_NOMEM, "out of host memory");
   std::string err;
@@ -146,7 +170,6 @@ int ugx_pattern_create(const uint32_t* opc, uint32_t nop, const ugx_prefilter* p
     rc = ugx::check_scope(p->dfa, *pf, matcher_flags, err);
   if (rc != UGX_OK)
   {
-    delete p;
     return fail(rc, err);
   }
   p->pf = *pf;
@@ -158,7 +181,6 @@ int ugx_pattern_create(const uint32_t* opc, uint32_t nop, const ugx_prefilter* p
   cudaError_t ce = cudaSetDevice(device);
   if (ce != cudaSuccess)
   {
-    delete p;
     return cuda_fail(ce, "cudaSetDevice (the scan path needs a CUDA device; there is no CPU fallback)");
   }
   ugx::DevPattern& d = p->dev;
@@ -228,7 +250,6 @@ int ugx_pattern_create(const uint32_t* opc, uint32_t nop, const ugx_prefilter* p
   if (rc == UGX_OK) p->allocs.push_back(d_words);
   if (rc != UGX_OK)
   {
-    delete p;
     return rc;
   }
   d.cls = d_cls;
@@ -238,11 +259,29 @@ int ugx_pattern_create(const uint32_t* opc, uint32_t nop, const ugx_prefilter* p
   d.pred = d_pred;
   d.tap = d_tap;
   d.word_ranges = d_words;
-  *out = p;
+  *out = holder.release();
   return UGX_OK;
 }
 
+static int plan_describe_impl(const uint32_t* opc, uint32_t nop, const ugx_prefilter* pf, uint32_t matcher_flags, ugx_plan_info* out);
+
 int ugx_plan_describe(const uint32_t* opc, uint32_t nop, const ugx_prefilter* pf, uint32_t matcher_flags, ugx_plan_info* out)
+{
+  try
+  {
+    return plan_describe_impl(opc, nop, pf, matcher_flags, out);
+  }
+  catch (const std::bad_alloc&)
+  {
+    return fail(UGX_E_NOMEM, "out of host memory");
+  }
+  catch (const std::exception& ex)
+  {
+    return fail(UGX_E_INVALID, std::string("ugx_plan_describe: ") + ex.what());
+  }
+}
+
+static int plan_describe_impl(const uint32_t* opc, uint32_t nop, const ugx_prefilter* pf, uint32_t matcher_flags, ugx_plan_info* out)
 {
   if (opc == nullptr || nop == 0 || pf == nullptr || out == nullptr)
     return fail(UGX_E_INVALID, "ugx_plan_describe: null argument");
@@ -296,8 +335,25 @@ int ugx_pattern_load(const char* path, int device, ugx_pattern** out)
             h.prefilter_size == sizeof(pf) && fread(&pf, sizeof(pf), 1, f) == 1;
   if (ok)
   {
-    opc.resize(h.nop);
-    ok = h.nop > 0 && fread(opc.data(), 4, h.nop, f) == h.nop;
+    // the opcode count comes from the file: it must fit in what is left of the file before anything is allocated
+    const long here = ftell(f);
+    ok = here >= 0 && fseek(f, 0, SEEK_END) == 0;
+    const long size = ok ? ftell(f) : -1;
+    ok = ok && size >= here && h.nop > 0 && static_cast<uint64_t>(h.nop) * 4 <= static_cast<uint64_t>(size - here) &&
+         fseek(f, here, SEEK_SET) == 0;
+  }
+  if (ok)
+  {
+    try
+    {
+      opc.resize(h.nop);
+    }
+    catch (const std::exception&)
+    {
+      fclose(f);
+      return fail(UGX_E_NOMEM, "out of host memory");
+    }
+    ok = fread(opc.data(), 4, h.nop, f) == h.nop;
   }
   fclose(f);
   if (!ok)
@@ -498,7 +554,7 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
   // a host buffer on the streaming route is copied chunk by chunk, overlapped with the scan, when every read of a
   // scanned position stays within one region of it: pure literals, and DFAs whose longest match is bounded
   const bool bounded = ugx::count_lines_literal_eligible(p->dev) || p->dfa.max_match_len < ugx::SC_REGION - 512;
-  const bool pipelined = stream_route && bounded && !s->no_pipeline && n >= 2 * PIPE_CHUNK && is_host_pointer(buf);
+  const bool pipelined = stream_route && bounded && !p->never && !s->no_pipeline && n >= 2 * PIPE_CHUNK && is_host_pointer(buf);
   int rc;
   if (pipelined)
   {
@@ -823,7 +879,7 @@ int ugx_scanner_fetch(ugx_scanner* s, ugx_match* out, uint64_t first, uint64_t c
 {
   if (s == nullptr || (out == nullptr && count != 0))
     return fail(UGX_E_INVALID, "null argument");
-  if (first + count > s->records_n)
+  if (first > s->records_n || count > s->records_n - first)
     return fail(UGX_E_INVALID, "record range outside the last result");
   if (count == 0)
     return UGX_OK;

@@ -175,6 +175,10 @@ __device__ __forceinline__ bool cand(const Text& t, const DevPattern& P, const T
       if (k + len + min > end || !literal_at(t, P, k))
         return false;
       return pmh(t, T.pred, k + len, min);
+    case UGX_ADV_NONE:
+      // advance_none (lib/matcher.cpp:957-960; option N with min_ == 0, :804) never moves the cursor: find() then
+      // attempts the DFA at every position in turn, which is what "every position is a candidate" gives
+      return true;
     default:
       return false;
   }

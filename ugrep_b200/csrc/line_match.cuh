@@ -361,6 +361,12 @@ __device__ inline uint32_t find_in_line(const Text& t, const DevPattern& P, cons
         return 0;
       if (m.cap != 0)
       {
+        if (P.flags & UGX_OPT_N)
+        {
+          // option N: the empty match is reported, the next find() starts one byte on (lib/matcher.cpp:715-721)
+          set_current(t, m, m.cur + 1, G);
+          return m.cap;
+        }
         if (!advance_to(t, P, T, cm, m, m.cur + 1, last, G))
           return 0;
         continue;

@@ -607,11 +607,6 @@ void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan)
 
 int check_scope(const HostDfa& dfa, const ugx_prefilter& pf, uint32_t matcher_flags, std::string& err)
 {
-  if (matcher_flags & UGX_OPT_N)
-  {
-    err = "matcher option N (empty matches, ugrep -Y) is outside the path's scope";
-    return UGX_E_UNSUPPORTED;
-  }
   if (dfa.newline_live)
   {
     err = "the DFA has a transition on '\\n': matches are not line-local";
