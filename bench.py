@@ -3,18 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2]
 
-One "step" = one pass of the hot path over one batch: `ugrep -c -F -f words.txt`
-(config c2, the 1,000-literal alternation) over a 4 GiB synthetic corpus per GPU.
-N > 1 is launched by torch.distributed.run, one rank per GPU; the corpus shards
-by line-aligned piece (one per rank, no data-path collective); NCCL only
-all-gathers the per-shard counts and newline counts (line-number bases).
+One "step" = one pass of the hot path over one batch.  Headline workload (every N): config c2,
+`ugrep -c -F -f words.txt` (the 1,000-literal alternation) over the DENSE 4 GiB-per-GPU corpus of
+SURVEY.md 8(d)-2.  N > 1 is launched by torch.distributed.run, one rank per GPU; the corpus shards by
+line-aligned piece, NCCL only all-gathers the per-shard {matches, newlines}.
 
-value  = whole-job GB/s with the corpus resident in HBM (CUDA events, max over ranks)
-e2e    = the same through the C ABI with HOST (pinned) buffers: H2D inside the timed region
-roofline / cpu_baseline: see DESIGN.md "measurement".
-
---impl reference times the reference's own CPU implementation (oracle/_ref/ugrep, the
-unmodified reference built from /root/reference) with all host cores on a bounded sample.
+value     whole-job GB/s with the corpus resident in HBM (CUDA events, max over ranks)
+e2e       the same through the C ABI with a HOST buffer: H2D + scan + D2H of the result inside the timed region
+          (pinned memory; `e2e.pageable` repeats it from ordinary pageable memory)
+roofline  the dominant kernel: algorithmic bytes (1 per corpus byte) / its own event-timed duration / measured HBM peak
+others    every other BASELINE config, timed the same way at its named size, each checked against the ORACLE on one
+          block (and by count additivity over the line-aligned tiling at full size).  c5 is the sharded config: the
+          logical corpus of N x 8 GiB is cut with sharding.tiled_cuts (forward to the next newline), rank r scans shard
+          r, and the all-gather of the counts sits INSIDE its timed region.
+--impl reference times the reference's own CPU implementation (oracle/_ref/ugrep, built unmodified from
+/root/reference) with all host cores on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -34,10 +37,11 @@ sys.path.insert(0, ROOT)
 
 GIB = 1 << 30
 
-# config -> (pattern file, corpus generator name, scan mode, reference CLI args, default GiB per GPU)
+# config -> (pattern file, corpus generator name, scan mode, reference CLI args, GiB per GPU the config names)
 CONFIGS = {
     "c1": ("c1", "c1", "lines", ["-c", "-F", "Sherlock Holmes"], 1),
     "c2": ("c2", "c2", "lines", ["-c", "-F", "-f", "@WORDS@"], 4),
+    "c2s": ("c2", "c2s", "lines", ["-c", "-F", "-f", "@WORDS@"], 4),
     "c3": ("c3", "c3", "list", ["-n", "-b", "-o", "[A-Z][a-z]+ing\\b"], 4),
     "c3b": ("c3b", "c3", "list", ["-n", "-b", "-o", "[A-Z][a-z]+ing"], 4),
     "c4": ("c4", "c4", "lines", ["-i", "-c", "\\p{Greek}+|naïve\\w*"], 8),
@@ -45,7 +49,8 @@ CONFIGS = {
 }
 WORKLOAD_TEXT = {
     "c1": "ugrep -c -F 'Sherlock Holmes' over synthetic ASCII text",
-    "c2": "ugrep -c -F -f words.txt (1,000-literal alternation) over synthetic text",
+    "c2": "ugrep -c -F -f words.txt (1,000-literal alternation) over the dense corpus (words drawn from the 1,000 needles and 20,000 like-made distractors: ~79% of lines match, ~23% of positions pass the prefilter)",
+    "c2s": "ugrep -c -F -f words.txt over the sparse corpus (<3% matching lines; distractors never contain a needle)",
     "c3": "ugrep -n -b -o '[A-Z][a-z]+ing\\b' (config 3 as named: the reference's prefilter admits no candidate, empty output) over synthetic text",
     "c3b": "ugrep -n -b -o '[A-Z][a-z]+ing' (match records) over synthetic text",
     "c4": "ugrep -i -c '\\p{Greek}+|naïve\\w*' over mixed UTF-8",
@@ -54,6 +59,8 @@ WORKLOAD_TEXT = {
 PAT_DIR = os.path.join(ROOT, "ugrep_b200", "patterns")
 REF_UGREP = os.path.join(ROOT, "oracle", "_ref", "ugrep")
 BLOCK_BYTES = 64 << 20
+HEADLINE = "c2"
+OTHERS_ORDER = ["c1", "c2s", "c3", "c3b", "c4", "c5"]
 
 
 def peaks():
@@ -95,33 +102,22 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def measured_traffic(cfg: str, kernel: str, nbytes: int):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json);
-    None unless the capture was taken on this workload size and kernel."""
+def capture_for(cfg: str, kernel: str, nbytes: int, kernel_ms: float):
+    """The committed `ncu --set full` capture of this config's dominant kernel (profiles/traffic.json), or None.  A
+    capture is only used when it was taken on this kernel, this workload size, and a launch whose duration under ncu
+    is consistent with today's event-timed one: ncu serialises and runs cold, so it may be slower, but a capture that
+    is more than 5 % FASTER than the live kernel, or more than 35 % slower, describes another kernel build."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f).get(cfg)
-        if t and t["kernel"] == kernel and t["nbytes"] == nbytes:
-            return int(t["dram_bytes_per_launch"])
+        if not t or t["kernel"] != kernel or t["nbytes"] != nbytes:
+            return None
+        ratio = t["gpu_time_ms"] / kernel_ms
+        if ratio < 0.95 or ratio > 1.35:
+            return None
+        return t
     except Exception:
-        pass
-    return None
-
-
-def measured_smem(cfg: str, kernel: str, nbytes: int):
-    """shared-memory lookup pressure of the dominant kernel from the same capture: LSU shared wavefronts per cycle per
-    SM (peak 1.0 = 128 B/clk/SM) and the share of them that are bank-conflict replays"""
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f).get(cfg)
-        if t and t["kernel"] == kernel and t["nbytes"] == nbytes and "smem_wavefronts_per_launch" in t:
-            wf = t["smem_wavefronts_per_launch"]
-            return {"wavefronts_per_clk_per_sm": round(wf / 148.0 / t["sm_cycles_per_launch"], 3), "peak": 1.0,
-                    "bank_conflict_share": round(t["smem_bank_conflict_wavefronts_per_launch"] / wf, 3),
-                    "wavefronts_per_kib": round(wf * 1024.0 / nbytes, 1), "source": t["source"]}
-    except Exception:
-        pass
-    return None
+        return None
 
 
 def make_block(cfg: str):
@@ -186,7 +182,7 @@ def reference_run(cfg: str, sample_bytes: int, steps: int, warmup: int):
                 count += int(tail)
         sec = sum(times) / len(times)
         return {"gbs": total / sec / 1e9, "seconds": sec, "cores": cores, "files": nfiles, "bytes": total,
-                "count": count, "best_gbs": total / min(times) / 1e9}
+                "count": count, "best_gbs": total / min(times) / 1e9, "warmup": warmup, "steps": steps}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
@@ -199,11 +195,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--config", default=HEADLINE, choices=list(CONFIGS))
     ap.add_argument("--gib", type=float, default=None, help="GiB per GPU (default: the config's named size)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--others", action="store_true", help="also time the other configs briefly (extra keys)")
+    ap.add_argument("--no-others", action="store_true", help="skip the other configs (quick runs, profiling)")
+    ap.add_argument("--others-gib", type=float, default=None, help="cap the other configs' size (GiB per GPU)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -218,14 +215,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sample = int(min(gib * GIB, 2 * GIB))
-        r = reference_run(cfg, sample, max(1, args.steps), max(1, min(args.warmup, 1)))
+        # a bounded sample (1 GiB) of the same workload; the warm-up and step counts are the ones asked for
+        sample = int(min(gib * GIB, 1 * GIB))
+        r = reference_run(cfg, sample, max(1, args.steps), max(0, args.warmup))
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ugrep is not built"}))
             return 0
         line = {
             "impl": "reference", "metric": "GB/s scanned", "value": round(r["gbs"], 3), "unit": "GB/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"],
             "ms_per_step": round(r["seconds"] * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "%s, %.2f GiB sample in %d line-aligned files" % (WORKLOAD_TEXT[cfg], r["bytes"] / GIB, r["files"]),
@@ -242,7 +240,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from ugrep_b200 import api
+    from ugrep_b200 import api, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the scan path is CUDA-only; there is no CPU fallback)")
@@ -255,27 +253,38 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        tm = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return float(tm.item())
+
+    stream = torch.cuda.current_stream().cuda_stream
+    sc = api.Scanner(local, stream)
+
+    def stepper(pat, mode):
+        def step(data):
+            if mode == "lines":
+                return sc.count_lines(pat, data)
+            if mode == "matches":
+                return sc.count_matches(pat, data)
+            return sc.find_all_device(pat, data)
+        return step
+
     # ---- corpus: one seeded block, tiled on the device to the named size (line-aligned, so still valid text)
     block = make_block(cfg)
     reps = max(1, int(gib * GIB) // block.size)
     nbytes = block.size * reps
     dblock = torch.from_numpy(block).cuda()
     corpus_dev = dblock.repeat(reps)
-    del dblock
     pat = api.Pattern.load(os.path.join(PAT_DIR, CONFIGS[cfg][0] + ".ugxp"), local)
-    stream = torch.cuda.current_stream().cuda_stream
-    sc = api.Scanner(local, stream)
     mode = CONFIGS[cfg][2]
+    step = stepper(pat, mode)
 
-    def step(data):
-        if mode == "lines":
-            return sc.count_lines(pat, data)
-        if mode == "matches":
-            return sc.count_matches(pat, data)
-        return sc.find_all_device(pat, data)
-
-    # expected result from one block (size-independent check: counts scale with the number of tiles)
-    t1 = step(torch.from_numpy(block).cuda())
+    # expected result: the block's count (checked against the oracle below on rank 0) times the number of tiles
+    t1 = step(dblock)
+    del dblock
     expect = t1.matches * reps
 
     for _ in range(args.warmup):
@@ -298,13 +307,8 @@ def main():
         launches += tot.launches
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     if world > 1:
-        tm = torch.tensor([ms], device="cuda")
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ms = float(tm.item())
-        # the one exchange step of the path: per-shard {matches, newlines} -> totals and line-number bases
-        from ugrep_b200 import sharding
         counts = sharding.all_gather_counts(tot.matches, tot.newlines, device="cuda")
         total_matches = sum(c[0] for c in counts)
     else:
@@ -312,59 +316,150 @@ def main():
     ms_per_step = ms / args.steps
     value = world * nbytes / (ms_per_step * 1e-3) / 1e9
 
-    # ---- e2e: host (pinned) buffer through the C ABI, H2D + scan + D2H of the result inside the timed region
+    # ---- e2e: host buffer through the C ABI, H2D + scan + D2H of the result inside the timed region
     e2e = None
     if not args.no_e2e:
+        def time_host(hb, esteps):
+            for _ in range(2):
+                th = step(hb)
+            if th.matches != expect:
+                raise SystemExit("bench.py: wrong e2e count")
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(esteps):
+                th = step(hb)
+            torch.cuda.synchronize()
+            return max_over_ranks(time.perf_counter() - t0)
+
         host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         hb = host.numpy()
         for i in range(reps):
             hb[i * block.size:(i + 1) * block.size] = block
-        for _ in range(2):
-            th = step(hb)
-        if th.matches != expect:
-            raise SystemExit("bench.py: wrong e2e count")
         esteps = max(3, min(args.steps, 5))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(esteps):
-            th = step(hb)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            tm = torch.tensor([dt], device="cuda")
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            dt = float(tm.item())
+        dt = time_host(hb, esteps)
         e2e = {"value": round(world * nbytes * esteps / dt / 1e9, 3), "unit": "GB/s",
-               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 32, "steps": esteps}
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 32, "steps": esteps, "host_memory": "pinned"}
         del host, hb
+        # the same from ordinary pageable memory (what an mmap'ing caller hands over without registering it)
+        pg = np.empty(nbytes, dtype=np.uint8)
+        for i in range(reps):
+            pg[i * block.size:(i + 1) * block.size] = block
+        dtp = time_host(pg, 2)
+        e2e["pageable"] = {"value": round(world * nbytes * 2 / dtp / 1e9, 3), "unit": "GB/s", "steps": 2}
+        del pg
 
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=2)
+    del corpus_dev
+    torch.cuda.empty_cache()
 
+    # ---- the other configs (same timing method; each checked against the oracle on one block)
+    oracle_check = None
     others = {}
-    if args.others and rank == 0:
-        for oc in CONFIGS:
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O  # the checker: CPU restatement of the path (test infrastructure)
+
+        def oracle_block(pfile, blk, m):
+            op = O.OraclePattern(os.path.join(PAT_DIR, pfile + ".ugxp"))
+            if m == "lines":
+                return op.count_lines(blk)
+            if m == "matches":
+                return op.count_matches(blk)
+            return op.find_all(blk)
+
+        want = oracle_block(CONFIGS[cfg][0], block, mode)
+        oracle_check = {"block_bytes": int(block.size), "gpu": int(t1.matches),
+                        "oracle": int(want if not hasattr(want, "__len__") else len(want))}
+        oracle_check["ok"] = oracle_check["gpu"] == oracle_check["oracle"]
+
+    def run_other(oc):
+        pfile, _, om, _, ogib = CONFIGS[oc]
+        if args.others_gib is not None:
+            ogib = min(ogib, args.others_gib)
+        ob = make_block(oc)
+        opat = api.Pattern.load(os.path.join(PAT_DIR, pfile + ".ugxp"), local)
+        ostep = stepper(opat, om)
+        dob = torch.from_numpy(ob).cuda()
+        res = {"workload": WORKLOAD_TEXT[oc]}
+        sharded = oc == "c5"
+        if sharded:
+            # one logical corpus of world x ogib GiB (+ one block, so that the nominal cuts fall inside lines), cut
+            # forward to the next newline; rank r materialises and scans shard r only
+            reps_total = world * max(1, int(ogib * GIB) // ob.size) + (1 if world > 1 else 0)
+            cuts = sharding.tiled_cuts(ob, reps_total, world)
+            lo, hi = cuts[rank], cuts[rank + 1]
+            od = sharding.materialize_tiled(dob, lo, hi)
+            res["sharding"] = {"logical_bytes": int(ob.size) * reps_total, "cuts": [int(c) for c in cuts],
+                               "cut_rule": "n*r/N forward to the next newline (sharding.tiled_cuts)"}
+        else:
+            if world > 1 and rank != 0:
+                return None
+            reps_total = max(1, int(ogib * GIB) // ob.size)
+            od = dob.repeat(reps_total)
+        tb = ostep(dob)   # the block alone: compared with the oracle on rank 0
+        rec_block = sc.fetch(0, tb.matches) if om == "list" else None
+        del dob
+        for _ in range(2):
+            t = ostep(od)
+        kms = []
+        nsteps = 5
+        if sharded:
+            barrier()
+        else:
+            torch.cuda.synchronize()
+        a0 = torch.cuda.Event(enable_timing=True)
+        a1 = torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(nsteps):
+            t = ostep(od)
+            kms.append(t.kernel_ms)
+            if sharded:
+                # the path's one exchange step, inside the timed region: per-shard {matches, newlines} -> totals, bases
+                counts = sharding.all_gather_counts(t.matches, t.newlines, device="cuda")
+        a1.record()
+        torch.cuda.synchronize()
+        oms = a0.elapsed_time(a1)
+        if sharded:
+            oms = max_over_ranks(oms)
+            total = sum(c[0] for c in counts)
+            logical = int(ob.size) * reps_total
+            bases = sharding.bases_from_counts(counts, cuts)
+            res["sharding"]["line_bases"] = [int(b[1]) for b in bases]
+        else:
+            total = t.matches
+            logical = int(od.numel())
+        k = sum(kms) / len(kms)
+        res.update({"gib_per_gpu": round(od.numel() / GIB, 3), "n_gpus": world if sharded else 1,
+                    "value": round(logical / (oms / nsteps * 1e-3) / 1e9, 2), "unit": "GB/s",
+                    "kernel": t.kernel, "kernel_ms": round(k, 4), "launches_per_step": t.launches,
+                    "frac": round(od.numel() / (k * 1e-3) / 1e9 / peak, 4), "count": int(total)})
+        if rank == 0:
+            want = oracle_block(pfile, ob, om)
+            if om == "list":
+                ok_block = len(want) == len(rec_block) and bool(np.all(want == rec_block))
+                want_n = len(want)
+            else:
+                ok_block = int(want) == int(tb.matches)
+                want_n = int(want)
+            res["oracle"] = {"block_bytes": int(ob.size), "block_count": want_n, "gpu_block_count": int(tb.matches),
+                             "tiles": reps_total, "ok": bool(ok_block and total == want_n * reps_total)}
+            if not res["oracle"]["ok"]:
+                raise SystemExit("bench.py: %s disagrees with the oracle: %r" % (oc, res))
+        del od
+        torch.cuda.empty_cache()
+        return res
+
+    if not args.no_others:
+        for oc in OTHERS_ORDER:
             if oc == cfg:
                 continue
-            ob = make_block(oc)
-            orep = max(1, (1 * GIB) // ob.size)
-            od = torch.from_numpy(ob).cuda().repeat(orep)
-            op = api.Pattern.load(os.path.join(PAT_DIR, CONFIGS[oc][0] + ".ugxp"), local)
-            om = CONFIGS[oc][2]
-            best = None
-            for _ in range(4):
-                if om == "lines":
-                    t = sc.count_lines(op, od)
-                elif om == "matches":
-                    t = sc.count_matches(op, od)
-                else:
-                    t = sc.find_all_device(op, od)
-                best = t.kernel_ms if best is None else min(best, t.kernel_ms)
-            gbs = od.numel() / (best * 1e-3) / 1e9
-            others[oc] = {"gbs": round(gbs, 2), "hbm_frac": round(gbs / peak, 4), "gib": round(od.numel() / GIB, 2),
-                          "result": t.matches}
-            del od
+            if world > 1 and oc != "c5":
+                continue  # under torchrun only the sharded config is timed besides the headline
+            r = run_other(oc)
+            if r is not None and rank == 0:
+                others[oc] = r
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -378,9 +473,18 @@ def main():
             cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % ex}
 
     if rank == 0:
+        if oracle_check is not None and not oracle_check["ok"]:
+            raise SystemExit("bench.py: the headline block count disagrees with the oracle: %r" % (oracle_check,))
         k_ms = sum(kernel_ms) / len(kernel_ms)
         achieved = nbytes / (k_ms * 1e-3) / 1e9
         info = pat.info
+        cap = capture_for(cfg, tot.kernel, nbytes, k_ms)
+        smem = None
+        if cap and "smem_wavefronts_per_launch" in cap:
+            wf = cap["smem_wavefronts_per_launch"]
+            smem = {"wavefronts_per_clk_per_sm": round(wf / 148.0 / cap["sm_cycles_per_launch"], 3), "peak": 1.0,
+                    "bank_conflict_share": round(cap["smem_bank_conflict_wavefronts_per_launch"] / wf, 3),
+                    "wavefronts_per_kib": round(wf * 1024.0 / nbytes, 1), "source": cap["source"]}
         line = {
             "metric": "GB/s scanned", "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
@@ -393,17 +497,17 @@ def main():
                        "table_in_smem": bool(info["table_in_smem"])},
             "hbm_frac": round(value / world / peak, 4),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": measured_traffic(cfg, tot.kernel, nbytes),
-                         "algorithmic_bytes": nbytes, "smem": measured_smem(cfg, tot.kernel, nbytes), "peak_kind": peak_kind,
+                         "frac": round(achieved / peak, 4),
+                         "traffic": int(cap["dram_bytes_per_launch"]) if cap else None,
+                         "algorithmic_bytes": nbytes, "smem": smem, "peak_kind": peak_kind,
                          "kernel": tot.kernel, "kernel_ms": round(k_ms, 4)},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": launches,
             "clocks": sampler.summary(),
-            "result": {"count": total_matches, "expected_per_gpu": expect},
+            "result": {"count": total_matches, "expected_per_gpu": expect, "oracle": oracle_check},
+            "others": others,
         }
-        if others:
-            line["others"] = others
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

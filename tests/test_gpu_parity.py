@@ -16,6 +16,7 @@ PAT_DIR = os.path.join(O.ROOT, "ugrep_b200", "patterns")
 CONFIGS = {
     "c1": ("c1", "c1", "lines"),
     "c2": ("c2", "c2", "lines"),
+    "c2s": ("c2", "c2s", "lines"),
     "c3": ("c3", "c3", "list"),
     "c3b": ("c3b", "c3", "list"),
     "c3c": ("c3c", "c3", "list"),
@@ -274,6 +275,23 @@ def test_pipelined_host_buffer_equals_device_scan(gpu):
             assert got.matches == reps * op.count_lines(block)
 
 
+def test_never_firing_prefilter_on_a_pipelined_host_buffer(gpu, tmp_path):
+    """a pattern whose bitap table admits no candidate (config 3's situation) with lbk == 0 and a bounded DFA, on a
+    host buffer big enough for the chunked H2D pipeline: the scan must still see the copied bytes (the newline count
+    it reports comes from the text)"""
+    api, sc = gpu
+    raw = bytearray(open(G.pattern_path("min2"), "rb").read())
+    tap_off = 24 + 12 * 4 + 256 + 256
+    raw[tap_off:tap_off + 2048] = b"\xff" * 2048
+    path = tmp_path / "never.ugxp"
+    path.write_bytes(bytes(raw))
+    pat = api.Pattern.load(str(path), 0)
+    host = np.tile(corpus.block("c1", 5 << 20), 14)   # 70 MiB > 2 pipeline chunks
+    t = sc.count_lines(pat, host)
+    assert t.matches == 0 and t.kernel == "count_newlines_kernel"
+    assert t.newlines == int((host == 10).sum())
+
+
 def test_count_newlines(gpu):
     """ugx_count_newlines = reflex::nlcount: every length around the 16-byte vectors, device and host buffers"""
     import torch
@@ -314,34 +332,42 @@ def test_misaligned_device_pointers_and_random_slices(gpu):
 
 def test_full_size_properties(gpu):
     """BASELINE-sized inputs, checked through size-independent properties: a corpus tiled from R line-aligned copies
-    of one seeded block must give R times the block's counts (the block's counts come from the oracle), and its match
-    records must be the block's records repeated with shifted offsets and line numbers."""
+    of one seeded block must give R times the block's counts (the block's counts come from the ORACLE), and its match
+    records must be the block's records repeated with shifted offsets and line numbers — including offsets and
+    record indices beyond 2^32 (c3b at 4.75 GiB)."""
     import torch
     api, sc = gpu
     block_bytes = 32 << 20
-    for pname, cname, mode, gib in (("c1", "c1", "lines", 4), ("c2", "c2", "lines", 2), ("c5", "c5", "matches", 1),
-                                    ("c3b", "c3", "list", 1)):
+    for pname, cname, mode, gib in (("c1", "c1", "lines", 4), ("c2", "c2", "lines", 4), ("c2", "c2s", "lines", 2),
+                                    ("c4", "c4", "lines", 8), ("c5", "c5", "matches", 8), ("c5", "c5", "lines", 2),
+                                    ("c3", "c3", "list", 4), ("c3b", "c3", "list", 4.75)):
         path = os.path.join(PAT_DIR, pname + ".ugxp")
         pat = api.Pattern.load(path, 0)
         op = O.OraclePattern(path)
         block = corpus.block(cname, block_bytes)
         assert block[-1] == 10
-        reps = (gib << 30) // len(block)
+        reps = int(gib * (1 << 30)) // len(block)
         dev = torch.from_numpy(block).cuda().repeat(reps)
+        nl = int((block == 10).sum())
         if mode == "lines":
-            assert sc.count_lines(pat, dev).matches == reps * op.count_lines(block), pname
+            assert sc.count_lines(pat, dev).matches == reps * op.count_lines(block), (pname, cname)
         elif mode == "matches":
-            assert sc.count_matches(pat, dev).matches == reps * op.count_matches(block), pname
+            t = sc.count_matches(pat, dev)
+            assert t.matches == reps * op.count_matches(block), pname
+            assert t.newlines == reps * nl, pname
         else:
             want = op.find_all(block)
-            tot = sc.find_all_device(pat, dev)
-            assert tot.matches == reps * len(want)
-            nl = int((block == 10).sum())
-            for r in (0, reps // 2, reps - 1):
-                got = sc.fetch(r * len(want), len(want))
-                assert bool(np.all(got["offset"] == want["offset"] + r * len(block))), (pname, r)
-                assert bool(np.all(got["line"] == want["line"] + r * nl)), (pname, r)
-                assert bool(np.all(got["len"] == want["len"])) and bool(np.all(got["cap"] == want["cap"])), (pname, r)
+            tot = sc.find_all_device(pat, dev, base_offset=7, base_line=3)
+            assert tot.matches == reps * len(want), pname
+            assert tot.newlines == reps * nl, pname
+            if len(want):
+                if gib > 4:
+                    assert int(want["offset"][-1]) + (reps - 1) * len(block) > 1 << 32
+                for r in (0, reps // 2, reps - 1):
+                    got = sc.fetch(r * len(want), len(want))
+                    assert bool(np.all(got["offset"] == want["offset"] + r * len(block) + 7)), (pname, r)
+                    assert bool(np.all(got["line"] == want["line"] + r * nl + 3)), (pname, r)
+                    assert bool(np.all(got["len"] == want["len"])) and bool(np.all(got["cap"] == want["cap"])), (pname, r)
         del dev
         torch.cuda.empty_cache()
 

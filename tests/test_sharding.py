@@ -29,6 +29,23 @@ def test_cut_points_are_line_aligned_and_cover_the_buffer():
     assert sharding.line_aligned_cuts(np.zeros(0, dtype=np.uint8), 2) == [0, 0, 0]
 
 
+def test_tiled_cuts_equal_the_cuts_of_the_materialised_corpus():
+    """bench.py shards a logical corpus (one block repeated R times) without building it on the host: the cuts
+    computed from the block alone, and the bytes materialised per shard, must equal the plain ones"""
+    import torch
+    block = corpus.block("c5", 50000)
+    tblock = torch.from_numpy(block)
+    for reps, world in ((1, 1), (3, 2), (9, 8), (17, 4), (8, 8), (5, 3)):
+        data = np.tile(block, reps)
+        cuts = sharding.tiled_cuts(block, reps, world)
+        assert cuts == sharding.line_aligned_cuts(data, world), (reps, world)
+        for r in range(world):
+            got = sharding.materialize_tiled(tblock, cuts[r], cuts[r + 1]).numpy()
+            assert got.tobytes() == data[cuts[r]:cuts[r + 1]].tobytes(), (reps, world, r)
+    with pytest.raises(ValueError):
+        sharding.tiled_cuts(np.frombuffer(b"no newline", dtype=np.uint8), 2, 2)
+
+
 def test_bases_from_gathered_counts():
     bases = sharding.bases_from_counts([(5, 10), (0, 3), (7, 0)], [0, 100, 250, 300])
     assert bases == [(0, 0, 0), (5, 10, 100), (5, 13, 250)]

@@ -20,10 +20,6 @@
 
 namespace ugx {
 
-namespace {
-
-} // namespace
-
 // MODE 0: count matching lines (ugrep -c), 1: count matches (ugrep -c -o) / emit records (ugrep -o)
 template <int MODE, bool EMIT, bool HAS_META, int THREADS>
 #ifndef UGX_SCAN_MINB

@@ -50,3 +50,48 @@ def all_gather_counts(matches: int, newlines: int, device=None) -> list[tuple[in
     allv = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
     dist.all_gather(allv, mine)
     return [(int(v[0]), int(v[1])) for v in allv]
+
+
+def tiled_cuts(block: np.ndarray, reps: int, world: int) -> list[int]:
+    """line_aligned_cuts() for the logical corpus ``block`` repeated ``reps`` times (``block`` ends with a newline),
+    computed from the block alone: the nominal cut n*r/world moves forward to the end of the line it falls in."""
+    B = int(block.size)
+    if B == 0 or block[-1] != 10:
+        raise ValueError("the block must end with a newline")
+    n = B * reps
+    nl = np.flatnonzero(block == 10)
+    cuts = [0]
+    for r in range(1, world):
+        target = max(cuts[-1], n * r // world)
+        if target >= n:
+            cuts.append(n)
+            continue
+        b, off = divmod(target, B)
+        if off == 0 or block[off - 1] == 10:
+            cuts.append(target)
+            continue
+        j = int(np.searchsorted(nl, off))          # first newline at or after `off`; the block's last byte is one
+        cuts.append(b * B + int(nl[j]) + 1)
+    cuts.append(n)
+    return cuts
+
+
+def materialize_tiled(dblock, lo: int, hi: int):
+    """bytes [lo, hi) of the logical corpus made of repetitions of the device tensor ``dblock``"""
+    import torch
+    B = int(dblock.numel())
+    parts = []
+    p = lo
+    if p < hi and p % B != 0:
+        take = min(B - p % B, hi - p)
+        parts.append(dblock[p % B:p % B + take])
+        p += take
+    whole = (hi - p) // B
+    if whole > 0:
+        parts.append(dblock.repeat(whole))
+        p += whole * B
+    if p < hi:
+        parts.append(dblock[:hi - p])
+    if not parts:
+        return dblock[:0].clone()
+    return torch.cat(parts) if len(parts) > 1 else parts[0].clone()
