@@ -152,7 +152,7 @@ typedef struct ugx_totals {
 
 /* scan kernels (reported in ugx_totals.kernel) */
 enum { UGX_K_NONE = 0, UGX_K_STREAM_LITERAL = 1, UGX_K_STREAM_DFA = 2, UGX_K_TILE_ANY = 3, UGX_K_LINE_SCAN = 4,
-       UGX_K_RECORDS = 5, UGX_K_NEWLINES = 6, UGX_K_MATCH_LINES = 7 };
+       UGX_K_RECORDS = 5, UGX_K_NEWLINES = 6, UGX_K_MATCH_LINES = 7, UGX_K_SPAN = 8 };
 
 const char *ugx_last_error(void);
 const char *ugx_kernel_name(uint32_t id);
@@ -178,7 +178,8 @@ void ugx_scanner_destroy(ugx_scanner *s);
  *   "count_newlines"  the streaming `-c` kernels also count newlines (totals.newlines)
  *   "match_lines"     counting takes the position-parallel-attempt kernel (match_lines.cu) instead of the line scan
  *   "two_pass_records" records by a count pass + an emit pass instead of the single-pass staging form
- *   "no_pipeline"     host buffers: one copy, then the scan (default: chunked copy overlapped with the scan) */
+ *   "no_pipeline"     host buffers: one copy, then the scan (default: chunked copy overlapped with the scan)
+ *   "no_span"         counting matches / records take the line-at-a-time kernels instead of the span kernels */
 int  ugx_scanner_set_option(ugx_scanner *s, const char *name, int value);
 
 /*

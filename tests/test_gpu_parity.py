@@ -174,7 +174,7 @@ def test_config_vs_reference_cli(gpu, name, cli):
 # ---- every committed golden case (made with the unmodified reference), through every kernel route ----
 import golden_lib as G  # noqa: E402
 
-ROUTES = {"default": {}, "generic": {"force_generic": 1}, "legacy_any": {"legacy_any": 1},
+ROUTES = {"default": {}, "generic": {"force_generic": 1}, "no_span": {"no_span": 1}, "legacy_any": {"legacy_any": 1},
           "stream": {"stream_dfa": 1}, "stream_nl": {"stream_dfa": 1, "count_newlines": 1},
           "two_pass": {"two_pass_records": 1}, "match_lines": {"match_lines": 1}}
 
@@ -201,9 +201,9 @@ def test_golden_cases(gpu, name, route):
         assert t.matches == case["lines"], (name, route, case["input"], "lines")
         if route == "stream_nl" and t.newlines:
             assert t.newlines == data.count(b"\n"), (name, case["input"], "newlines")
-        if route in ("default", "generic", "match_lines"):
+        if route in ("default", "generic", "match_lines", "no_span"):
             assert sc.count_matches(pat, data).matches == case["matches"], (name, route, case["input"], "matches")
-        if route == "default":
+        if route in ("default", "no_span"):
             rec, _ = sc.find_all(pat, data)
             assert len(rec) == case["matches"]
             G.check_list(case, data, rec)
@@ -370,6 +370,57 @@ def test_full_size_properties(gpu):
                     assert bool(np.all(got["len"] == want["len"])) and bool(np.all(got["cap"] == want["cap"])), (pname, r)
         del dev
         torch.cuda.empty_cache()
+
+
+def test_long_lines_are_scanned_by_all_warps(gpu):
+    """lines far longer than a region (here: one line of 8 MiB with records, one of 256 MiB with counts) go through
+    the span kernels like any other text — regions take their chain state from the 512 bytes before them — and must
+    equal the oracle's sequential find loop; a throughput floor guards against a one-thread fallback"""
+    import torch
+    api, sc = gpu
+    path = os.path.join(PAT_DIR, "c5.ugxp")
+    pat = api.Pattern.load(path, 0)
+    op = O.OraclePattern(path)
+    base = corpus.block("c5", 32 << 20).copy()
+    base[base == 10] = 32
+    small = base[:8 << 20].copy()
+    small[-5:] = np.frombuffer(b" end\n", dtype=np.uint8)
+    rec, tot = sc.find_all(pat, small)
+    assert tot.kernel == "span_scan_kernel"
+    want = op.find_all(small)
+    assert len(want) > 100000 and same(rec, want)
+    assert int(rec["line"].max()) == 1
+    big = np.tile(base, 8)
+    big[-5:] = np.frombuffer(b" end\n", dtype=np.uint8)
+    dev = torch.from_numpy(big).cuda()
+    t = sc.count_matches(pat, dev)
+    assert t.kernel == "span_scan_kernel" and t.newlines == 1
+    assert t.matches == op.count_matches(big) and t.matches > 1000000
+    best = min(sc.count_matches(pat, dev).kernel_ms for _ in range(3))
+    assert big.size / best / 1e6 >= 50.0, "%.1f GB/s on a single 256 MiB line" % (big.size / best / 1e6)
+
+
+def test_span_kernels_hand_over_what_they_cannot_vouch_for(gpu):
+    """inputs outside the span kernels' guarantees must come back exact through the line-at-a-time kernels: a match
+    longer than a window across a region start inside a long line, a look-back run longer than the look-ahead bound,
+    a match of 64 KiB or more, an attempt that fails at the very end of a long last line"""
+    api, sc = gpu
+    cases = [
+        ("dotstar", b"x" * 20000 + b"a" + b"y" * 40000 + b"b zz a b\n" + b"a b\n" * 10),
+        ("pin_pma_lb", b"the s" + b"a" * 50000 + b"ing sing\nsing song\n"),
+        ("dotstar", b"a" + b"q" * 70000 + b"b\n" + b"ab\n" * 5),
+        ("c5", b"x" * 100000 + b" ERROR 555-12"),
+    ]
+    for name, data in cases:
+        path = G.pattern_path(name) if name != "c5" else os.path.join(PAT_DIR, "c5.ugxp")
+        pat = api.Pattern.load(path, 0)
+        op = O.OraclePattern(path)
+        rec, tot = sc.find_all(pat, data)
+        assert same(rec, op.find_all(data)), name
+        assert sc.count_matches(pat, data).matches == op.count_matches(data), name
+    # ... and the ordinary case does stay with the spans
+    pat = api.Pattern.load(os.path.join(PAT_DIR, "c5.ugxp"), 0)
+    assert sc.count_matches(pat, corpus.block("c5", 1 << 20)).kernel == "span_scan_kernel"
 
 
 def test_scanners_on_two_host_threads_share_a_pattern(gpu):

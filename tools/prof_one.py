@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from ugrep_b200 import api, corpus  # noqa: E402
 
-CFG = {"c1": ("c1", "c1", "lines"), "c2": ("c2", "c2", "lines"), "c3b": ("c3b", "c3", "list"),
+CFG = {"c3bl": ("c3b", "c3", "lines"), "c1": ("c1", "c1", "lines"), "c2": ("c2", "c2", "lines"), "c2s": ("c2", "c2s", "lines"), "c3b": ("c3b", "c3", "list"),
        "c3c": ("c3c", "c3", "list"), "c4": ("c4", "c4", "lines"), "c5": ("c5", "c5", "matches"),
        "c5l": ("c5", "c5", "lines"), "c3bm": ("c3b", "c3", "matches")}
 

@@ -127,6 +127,10 @@ struct ugx_scanner {
   unsigned long long* partials = nullptr; // [2 * STREAM_MAX_GRID]
   unsigned long long* ticket = nullptr;   // {ticket (u64), done (u32)}
   uint64_t stage_cap = 0;
+  // span scan scratch
+  uint64_t* span_regions = nullptr; // [5 * regions]
+  uint64_t span_regions_cap = 0;
+  bool no_span = false;           // counting matches / records take the line-at-a-time kernels (A/B timing, tests)
 };
 
 extern "C" {
@@ -406,9 +410,9 @@ int ugx_scanner_create(int device, void* stream, ugx_scanner** out)
   if (e == cudaSuccess)
     e = cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming);
   if (e == cudaSuccess)
-    e = cudaMalloc(reinterpret_cast<void**>(&s->totals), 4 * sizeof(unsigned long long));
+    e = cudaMalloc(reinterpret_cast<void**>(&s->totals), 8 * sizeof(unsigned long long));
   if (e == cudaSuccess)
-    e = cudaMallocHost(reinterpret_cast<void**>(&s->h_totals), 4 * sizeof(unsigned long long));
+    e = cudaMallocHost(reinterpret_cast<void**>(&s->h_totals), 8 * sizeof(unsigned long long));
   if (e == cudaSuccess)
     e = cudaMalloc(reinterpret_cast<void**>(&s->partials), 2 * ugx::STREAM_MAX_GRID * sizeof(unsigned long long));
   if (e == cudaSuccess)
@@ -436,6 +440,7 @@ void ugx_scanner_destroy(ugx_scanner* s)
   cudaFree(s->totals);
   cudaFreeHost(s->h_totals);
   cudaFree(s->region_sum);
+  cudaFree(s->span_regions);
   cudaFree(s->tile_base);
   cudaFree(s->rec_stage);
   cudaFree(s->partials);
@@ -525,6 +530,61 @@ bool is_host_pointer(const void* buf)
   return at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged;
 }
 
+// `ugrep -c -o` / `ugrep -o -n -b` through the span kernels (span_scan.cu).  *valid = false: the spans could not vouch
+// for their result on this buffer (a match longer than a window across a region start in a line without newlines, an
+// attempt that failed at the very end of the buffer, a match of 64 KiB or more) — the caller then takes the
+// line-at-a-time kernels.
+int scan_spans(ugx_scanner* s, const ugx_pattern* p, const uint8_t* dbuf, uint64_t n, bool want_records, uint64_t base_offset,
+               uint64_t base_line, ugx_totals* tt, bool* valid)
+{
+  *valid = false;
+  const uint64_t nreg = ugx::stream_regions(n);
+  int rc = ensure(s->span_regions, s->span_regions_cap, 5 * nreg + 8);
+  if (rc != UGX_OK)
+    return rc;
+  ugx::SpanArgs a;
+  memset(&a, 0, sizeof(a));
+  a.reg_matches = s->span_regions;
+  a.reg_newlines = s->span_regions + nreg;
+  a.reg_emain = s->span_regions + 2 * nreg;
+  a.reg_elast = s->span_regions + 3 * nreg;
+  a.reg_v = s->span_regions + 4 * nreg;
+  a.base_offset = base_offset;
+  a.base_line = base_line;
+  a.tail = reinterpret_cast<const uint64_t*>(s->totals + 5);
+  a.flags = reinterpret_cast<unsigned int*>(s->totals + 6);
+  CU(cudaMemsetAsync(s->totals + 6, 0, sizeof(unsigned long long), s->stream));
+  CU(ugx::launch_last_line(dbuf, n, reinterpret_cast<uint64_t*>(s->totals + 5), s->stream));
+  CU(ugx::launch_span_scan(p->dev, dbuf, n, a, false, s->sm_count, s->stream));
+  CU(ugx::launch_span_final(p->dev, dbuf, n, a, false, s->totals, s->stream));
+  CU(cudaMemcpyAsync(s->h_totals, s->totals, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  tt->launches += 3;
+  if (s->h_totals[2] != 0)
+    return UGX_OK; // not valid: nothing of this attempt is used
+  const uint64_t nrec = s->h_totals[0];
+  if (want_records)
+  {
+    rc = ensure(s->records, s->records_cap, nrec);
+    if (rc != UGX_OK)
+      return rc;
+    if (nrec > 0)
+    {
+      a.out = s->records;
+      a.out_cap = nrec;
+      CU(ugx::launch_span_scan(p->dev, dbuf, n, a, true, s->sm_count, s->stream));
+      CU(ugx::launch_span_final(p->dev, dbuf, n, a, true, s->totals, s->stream));
+      tt->launches += 2;
+    }
+    s->records_n = nrec;
+  }
+  tt->matches = nrec;
+  tt->newlines = s->h_totals[1];
+  tt->kernel = UGX_K_SPAN;
+  *valid = true;
+  return UGX_OK;
+}
+
 int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t n, int mode, bool want_records,
                 uint64_t base_offset, uint64_t base_line, const ugx_match** dev_out, uint64_t* n_out, ugx_totals* totals)
 {
@@ -584,6 +644,34 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
     if (totals)
       *totals = tt;
     return UGX_OK;
+  }
+  if (mode == 1 && !s->force_generic && !s->no_span && !s->match_lines && !s->two_pass_records &&
+      ugx::span_scan_eligible(p->dev))
+  {
+    bool valid = false;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    rc = scan_spans(s, p, dbuf, n, want_records, base_offset, base_line, &tt, &valid);
+    if (rc != UGX_OK)
+      return rc;
+    if (valid)
+    {
+      CU(cudaEventRecord(s->ev1, s->stream));
+      CU(cudaStreamSynchronize(s->stream));
+      float sms = 0;
+      CU(cudaEventElapsedTime(&sms, s->ev0, s->ev1));
+      tt.kernel_ms = sms;
+      if (want_records)
+      {
+        if (n_out)
+          *n_out = s->records_n;
+        if (dev_out)
+          *dev_out = s->records;
+      }
+      if (totals)
+        *totals = tt;
+      return UGX_OK;
+    }
+    tt.launches = 0; // the line-at-a-time kernels take over
   }
   const uint64_t tile_bytes = ugx::scan_tile_bytes(p->dev);
   const uint64_t ntiles = (n + tile_bytes - 1) / tile_bytes;
@@ -829,6 +917,7 @@ const char* ugx_kernel_name(uint32_t id)
     case UGX_K_RECORDS: return "scan_records_kernel";
     case UGX_K_NEWLINES: return "count_newlines_kernel";
     case UGX_K_MATCH_LINES: return "match_lines_kernel";
+    case UGX_K_SPAN: return "span_scan_kernel";
     default: return "none";
   }
 }
@@ -865,6 +954,11 @@ int ugx_scanner_set_option(ugx_scanner* s, const char* name, int value)
   if (strcmp(name, "stream_dfa") == 0)
   {
     s->stream_dfa = value != 0;
+    return UGX_OK;
+  }
+  if (strcmp(name, "no_span") == 0)
+  {
+    s->no_span = value != 0;
     return UGX_OK;
   }
   if (strcmp(name, "count_newlines") == 0)

@@ -89,6 +89,30 @@ cudaError_t launch_reorder_records(const ugx_match* stage, ugx_match* out, const
                                    const uint64_t* tile_base, uint64_t ntiles, const unsigned long long* totals,
                                    uint64_t base_line, int sm_count, cudaStream_t st);
 
+// ---- span scan (span_scan.cu): `ugrep -c -o` / `ugrep -o -n -b` with every DFA attempt taken out of the find loop ----
+constexpr uint64_t SPAN_TAIL_MAX = 65536;   // a last line up to this long is left to the final kernel's line-at-a-time form
+
+struct SpanArgs {
+  uint64_t* reg_matches;   // [regions] count pass: matches that start in the region; after the final kernel: exclusive prefix
+  uint64_t* reg_newlines;  // [regions] likewise, newlines
+  uint64_t* reg_emain;     // [regions] farthest end of a success that starts in spans 0..30 of the region
+  uint64_t* reg_elast;     // [regions] ... in its last span (the next region's window)
+  uint64_t* reg_v;         // [regions] validation point of the region's chain start (~0 = none needed)
+  ugx_match* out;          // emit pass: records in input order
+  uint64_t out_cap;
+  uint64_t base_offset, base_line;
+  const uint64_t* tail;    // device: [0] = start of the last line (the spans scan [0, tail[0]))
+  unsigned int* flags;     // device: bit 0 an attempt failed at the end of the buffer, bit 1 a match too long for the span tables
+  uint32_t stage_table;    // set by the launcher
+};
+
+bool span_scan_eligible(const DevPattern& P);
+cudaError_t launch_last_line(const uint8_t* buf, uint64_t n, uint64_t* tail, cudaStream_t st);
+cudaError_t launch_span_scan(const DevPattern& P, const uint8_t* buf, uint64_t n, SpanArgs a, bool emit, int sm_count,
+                             cudaStream_t st);
+cudaError_t launch_span_final(const DevPattern& P, const uint8_t* buf, uint64_t n, const SpanArgs& a, bool emit,
+                              unsigned long long* totals, cudaStream_t st);
+
 // reflex::nlcount (newline_count.cu)
 cudaError_t launch_count_newlines(const uint8_t* buf, uint64_t n, unsigned long long* total, int sm_count, cudaStream_t st);
 

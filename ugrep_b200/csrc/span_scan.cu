@@ -1,0 +1,772 @@
+// span_scan.cu — span_scan_kernel: `ugrep -c -o` (count matches) and `ugrep -o -n -b` (match records) as a
+// streaming pass in which every DFA attempt is taken OUT of the sequential find loop, for patterns with or without
+// look-back, and in which lines of any length are scanned by many warps at once.
+//
+// The rule it implements (checked against the oracle's find loop on the CPU, tests/test_span_rule.py).  For a
+// pattern without META edges, without option W and whose start state does not accept, successive calls of
+// Matcher::match(FIND) (lib/matcher.cpp:42-750) over a buffer return exactly the chain
+//
+//     c -> the first p >= c with p in A and D(p) > 0;   c := p + D(p)
+//
+//   D(p) = length of the longest match of the DFA anchored at p (0 = none): a function of the text alone;
+//   A    = { p : some prefilter candidate k >= p has only look-back bytes (cbk_) in [p, k) } — the positions the
+//          look-back / retry rules (lib/matcher.cpp:54-70, 627-658) can attempt: after a candidate k the matcher
+//          walks back over the cbk_ run below k and then tries every position of that run up to k in increasing
+//          order (first by its retry budget, then — budget spent — by advancing again with the floor one byte on),
+//          so within one find() the attempted positions are A at or after the cursor, in order.  Without look-back
+//          A is the candidate set.  A is position-local: A(p) = cand(p) | (cbk(p) & A(p + 1)), a carry chain that
+//          runs from high to low addresses.
+//
+// Work decomposition.  The buffer is cut into 16 KiB regions; a warp owns the matches that START in its region.  It
+// walks the region in 512-byte spans, lane l holding chunk l (16 bytes + halo) of the span:
+//   1. masks    candidate / look-back / newline bits of the 16 positions (register window, tile_phase_a.cuh);
+//   2. A        the carry chain within the lane (a 16-bit add), across lanes (a 64-bit add of two ballots) and across
+//               spans (the next span's masks are evaluated one iteration ahead);
+//   3. D        the positions of A are compacted into a per-warp queue and handed out one per lane, so the attempts
+//               run with full warps whatever their distribution; results go to a per-warp table in shared memory;
+//   4. chain    every lane resolves its own successes assuming the cursor reaches it before its first success; one
+//               shuffle checks the assumption for all lanes; spans in which a match straddles into a lane's first
+//               success (rare) are resolved lane after lane instead.
+// The chain state at a region start comes from the 512 bytes before it (the "window"): after a newline in the window
+// the chain is fresh (no match crosses a newline: no DFA in scope has a '\n' transition); without one it is taken fresh
+// from the window's first success, which is right unless a match that starts before the window reaches beyond that
+// point — every region publishes the farthest end of its matches and the final kernel checks exactly that condition;
+// a violation (a match longer than 512 bytes straddling a region start inside a line longer than 512 bytes) makes the
+// caller fall back to the line-at-a-time kernels for this buffer.  Hence a 1 GiB line is scanned by all warps.
+//
+// End of the buffer.  A failed attempt that read up to the end of the buffer makes the reference continue byte by
+// byte without its prefilter (lib/matcher.cpp:623 `if (!at_end())`, :709-713).  Only attempts in the last line can
+// do that.  The last line (when it is at most 64 KiB long) is therefore left to one thread of the final kernel, which
+// runs the line-at-a-time form (find_in_line) on it; a longer last line stays with the spans and an attempt that
+// fails at the end of the buffer raises the same fallback flag.
+#include "block_scan.cuh"
+#include "device_pattern.cuh"
+#include "line_match.cuh"
+#include "ptx.cuh"
+#include "scan_kernels.hpp"
+#include "tile_phase_a.cuh"
+
+namespace ugx {
+
+namespace {
+
+constexpr uint32_t SP_SPAN = 512;
+constexpr int SP_SPANS = SC_REGION / SP_SPAN; // spans per region
+constexpr uint32_t SP_LONG = 0xffffu;         // D(p) is kept in 16 bits
+constexpr uint64_t SP_NO_V = ~0ull;           // region needs no validation (its chain starts after a newline)
+constexpr uint32_t SP_FAR_SPANS = 64;         // longest look-ahead over a run of look-back bytes (32 KiB)
+
+struct SpanMasks {
+  uint32_t cand, cbk, nl; // 16 bits each: bit k = byte k of the lane's chunk
+};
+
+// masks of the chunk at `base` (16-byte aligned); positions at or past `limit` read as nothing
+__device__ __forceinline__ SpanMasks eval_masks(const Text& t, const DevPattern& P, const Tables& T, const uint8_t* s_flags,
+                                                uint64_t base, uint64_t limit, bool want_cbk)
+{
+  SpanMasks m;
+  m.cand = m.cbk = m.nl = 0;
+  if (base >= limit)
+    return m;
+  Window W;
+  const bool interior = load_window(t.b, t.end, base, W);
+  m.cand = interior ? chunk_cand_fast(W, t, P, T, base) : chunk_cand_generic(t, P, T, base);
+  m.nl = newline_mask16(W);
+  if (want_cbk)
+  {
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      m.cbk |= static_cast<uint32_t>(s_flags[UGX_WB(W, k)] & 1u) << k;
+  }
+  if (base + 16 > limit)
+  {
+    const uint32_t valid = (1u << (limit - base)) - 1u;
+    m.cand &= valid;
+    m.cbk &= valid;
+    m.nl &= valid;
+  }
+  return m;
+}
+
+// A(p) = C(p) | (R(p) & A(p + 1)) over the 16 positions of a chunk; cin = A(position 16); cout = A(position 0)
+__device__ __forceinline__ uint32_t flood16(uint32_t C, uint32_t R, uint32_t cin, uint32_t& cout)
+{
+  const uint32_t c = __brev(C) >> 16, r = __brev(R) >> 16; // reversed: the carry now runs upwards
+  const uint32_t a = c | r;
+  const uint32_t sum = a + c + cin;
+  const uint32_t K = sum ^ a ^ c;                         // carry into every bit
+  cout = (K >> 16) & 1u;
+  return __brev((c | (r & K)) & 0xffffu) >> 16;
+}
+
+// lane-level carry behaviour of a span: G = lanes whose position 0 is in A whatever comes in, Pp = lanes that only
+// pass the carry on (all 16 bytes look-back bytes, no candidate)
+struct SpanCarry {
+  uint32_t G, Pp;
+  // A(first position of the span) given the carry into its last lane
+  __device__ __forceinline__ uint32_t out(uint32_t cin) const
+  {
+    const uint32_t g = __brev(G), a = g | __brev(Pp);
+    return static_cast<uint32_t>((static_cast<uint64_t>(a) + g + cin) >> 32);
+  }
+  // the carry into lane `lane`
+  __device__ __forceinline__ uint32_t into(uint32_t cin, uint32_t lane) const
+  {
+    const uint32_t g = __brev(G), a = g | __brev(Pp);
+    const uint32_t K = static_cast<uint32_t>(static_cast<uint64_t>(a) + g + cin) ^ a ^ g;
+    return (K >> (31u - lane)) & 1u;
+  }
+};
+
+__device__ __forceinline__ SpanCarry span_carry(const SpanMasks& m)
+{
+  uint32_t g;
+  flood16(m.cand, m.cbk, 0u, g);
+  SpanCarry c;
+  c.G = __ballot_sync(0xffffffffu, g != 0);
+  c.Pp = __ballot_sync(0xffffffffu, m.cbk == 0xffffu && m.cand == 0);
+  return c;
+}
+
+// one anchored attempt: (accept << 16) | length, 0 = no match.  `flags`: bit 0 the attempt failed after reading up to
+// the end of the buffer, bit 1 the match does not fit 16 bits (or its accept index 15 bits)
+__device__ __forceinline__ uint32_t attempt_span(const Text& t, const DevPattern& P, const Tables& T, uint64_t pos, uint32_t& flags)
+{
+  if (P.one)
+  {
+    if (P.len >= SP_LONG)
+      flags |= 2u;
+    return (1u << 16) | P.len; // the candidate test was the exact literal (lib/matcher.cpp:71-83)
+  }
+  uint32_t state = 0, best = 0;
+  uint64_t p = pos;
+  const uint32_t first_acc = P.first_acc, ncls = P.ncls;
+  for (;;)
+  {
+    if (p >= t.end)
+      break;
+    const uint32_t ch = t.raw(p++);
+    const uint32_t nxt = T.next[state * ncls + T.cls[ch]];
+    if (nxt == D_DEAD)
+      break;
+    if (nxt >= first_acc)
+    {
+      const uint32_t acc = __ldg(P.accept + nxt);
+      if ((acc & 0x7fffffffu) != 0)
+      {
+        const uint64_t len = p - pos;
+        if (len >= SP_LONG || (acc & 0x7fffffffu) >= 0x8000u)
+          flags |= 2u;
+        best = ((acc & 0x7fffu) << 16) | static_cast<uint32_t>(len & 0xffffu);
+      }
+      if (acc & 0x80000000u) // no outgoing edges: the interpreter halts here before reading
+        return best;
+    }
+    state = nxt;
+  }
+  if (best == 0 && p >= t.end)
+    flags |= 1u;
+  return best;
+}
+
+struct RegionOut {
+  uint64_t matches, newlines, emain, elast, v;
+};
+
+} // namespace
+
+// the start of the buffer's last line, if that line is at most SPAN_TAIL_MAX bytes long: tail[0] = its offset, else n
+__global__ void __launch_bounds__(32) last_line_kernel(const uint8_t* __restrict__ buf, uint64_t n, uint64_t* __restrict__ tail)
+{
+  const uint32_t lane = threadIdx.x;
+  uint64_t t0 = n;
+  if (n > 0)
+  {
+    // the last byte does not end a PREVIOUS line even when it is a newline: search [n - 1 - MAX, n - 1)
+    const uint64_t hi = n - 1;
+    const uint64_t lo = hi > SPAN_TAIL_MAX ? hi - SPAN_TAIL_MAX : 0;
+    uint64_t at = hi;
+    bool found = false;
+    while (at > lo && !found)
+    {
+      const uint64_t from = at - lo > 32 * 8 ? at - 32 * 8 : lo; // 256 bytes per step
+      uint32_t best = 0;
+      bool mine = false;
+      for (uint64_t i = from + lane * 8; i < at && i < from + lane * 8 + 8; ++i)
+        if (__ldg(buf + i) == '\n')
+        {
+          mine = true;
+          best = static_cast<uint32_t>(i - from);
+        }
+      const uint32_t any = __ballot_sync(0xffffffffu, mine);
+      if (any != 0)
+      {
+        const uint32_t src = 31u - __clz(any);
+        t0 = from + __shfl_sync(0xffffffffu, best, src) + 1;
+        found = true;
+      }
+      at = from;
+    }
+    if (!found)
+      t0 = lo == 0 ? 0 : n; // the whole buffer is one short line, or the last line is too long to set aside
+  }
+  if (lane == 0)
+    tail[0] = t0;
+}
+
+// EMIT false: per region {matches that start in it, newlines in it, farthest match ends, validation point};
+// EMIT true:  the same walk writing records; reg_matches / reg_newlines then hold the exclusive prefixes
+template <bool EMIT, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 1 : 4)
+span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, SpanArgs a)
+{
+  constexpr uint32_t NWARPS = THREADS / 32;
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  uint8_t* s_cls = smem;
+  uint8_t* s_pred = s_cls + 256;
+  uint8_t* s_tap = s_pred + UGX_HASH;
+  uint8_t* s_flags = s_tap + UGX_BTAP;                                     // [256] bit 0: look-back byte
+  uint32_t* s_dtab = reinterpret_cast<uint32_t*>(s_flags + 256);           // [NWARPS][512] (accept << 16) | length
+  uint32_t* s_succ = s_dtab + NWARPS * SP_SPAN;                            // [NWARPS][16] success bits of the span
+  uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_succ + NWARPS * 16);   // [NWARPS][512] attempt positions
+  uint16_t* s_next = s_queue + NWARPS * SP_SPAN;
+  stage_tables_bulk(&s_bar, s_cls, P.cls, s_pred, P.pred, s_tap, P.tap, s_next, P.next,
+                    a.stage_table ? ((P.table_bytes + 15) / 16) * 16 : 0);
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
+    s_flags[i] = bit256(P.cbk, i) ? 1u : 0u;
+  for (uint32_t i = threadIdx.x; i < NWARPS * 16; i += blockDim.x)
+    s_succ[i] = 0;
+  __syncthreads();
+  Tables T;
+  T.cls = s_cls;
+  T.pred = s_pred;
+  T.tap = s_tap;
+  T.next = a.stage_table ? s_next : P.next;
+  const Text t{buf, n};
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t* dtab = s_dtab + wid * SP_SPAN;
+  uint32_t* succ = s_succ + wid * 16;
+  uint16_t* queue = s_queue + wid * SP_SPAN;
+  const bool has_lb = P.lbk != 0;
+  const uint64_t limit = __ldcg(a.tail); // spans own [0, limit): the last line belongs to the final kernel
+  const uint64_t nregions = (limit + SC_REGION - 1) / SC_REGION;
+  const uint64_t total_warps = static_cast<uint64_t>(gridDim.x) * NWARPS;
+  uint32_t bad = 0; // bit 0: an attempt failed at the end of the buffer, bit 1: a match too long for the table
+
+  for (uint64_t r = static_cast<uint64_t>(blockIdx.x) * NWARPS + wid; r < nregions; r += total_warps)
+  {
+    const uint64_t rb = r * SC_REGION;
+    uint64_t m_run = 0, nl_run = 0;   // matches / newlines of the region so far (warp-uniform)
+    uint64_t emain = 0, elast = 0;    // lane-private: farthest end of a success that starts in spans 0..30 / span 31
+    uint64_t vpoint = SP_NO_V;
+    int64_t cursor = 0;               // chain cursor, relative to the current span's base (warp-uniform)
+    uint64_t far_base = 0;            // look-ahead cache: the carry out of the run that ends in the span at far_base
+    uint32_t far_val = 0;
+    uint64_t out_base = 0, line_base = 0;
+    if (EMIT)
+    {
+      out_base = a.reg_matches[r];
+      line_base = a.reg_newlines[r] + 1 + a.base_line;
+    }
+    // masks of the first span to process (the window before the region, or span 0 of region 0) and of the one after
+    int s = r == 0 ? 0 : -1;
+    SpanMasks cur = eval_masks(t, P, T, s_flags, rb + static_cast<int64_t>(s) * SP_SPAN + lane * 16, limit, has_lb);
+    for (; s < SP_SPANS; ++s)
+    {
+      const uint64_t sbase = rb + static_cast<int64_t>(s) * SP_SPAN;
+      if (sbase >= limit)
+        break;
+      // ---- 1. masks of the next span (needed now for the carry into this one; they become `cur` afterwards)
+      const SpanMasks nxt = eval_masks(t, P, T, s_flags, sbase + SP_SPAN + lane * 16, limit, has_lb);
+      // ---- 2. the attempt set of this span
+      uint32_t a16 = cur.cand;
+      if (has_lb)
+      {
+        const SpanCarry cn = span_carry(nxt);
+        uint32_t cin_span = cn.out(0);
+        if (cn.out(1) != cin_span)
+        {
+          // 512 look-back bytes in a row without a candidate: look further ahead until the run ends.  The answer holds
+          // for every span up to there (they all just pass the carry on), so it is kept; the look-ahead is bounded —
+          // a longer run leaves the buffer to the line-at-a-time kernels.
+          if (far_base <= sbase + SP_SPAN)
+          {
+            far_val = 0;
+            far_base = limit;
+            uint32_t steps = 0;
+            for (uint64_t fb = sbase + 2 * SP_SPAN; fb < limit; fb += SP_SPAN)
+            {
+              if (++steps > SP_FAR_SPANS)
+              {
+                bad |= 4u;
+                break;
+              }
+              const SpanMasks far = eval_masks(t, P, T, s_flags, fb + lane * 16, limit, true);
+              const SpanCarry cf = span_carry(far);
+              const uint32_t o0 = cf.out(0);
+              if (cf.out(1) == o0)
+              {
+                far_val = o0;
+                far_base = fb;
+                break;
+              }
+            }
+          }
+          cin_span = far_val;
+        }
+        const SpanCarry cc = span_carry(cur);
+        uint32_t unused;
+        a16 = flood16(cur.cand, cur.cbk, cc.into(cin_span, lane), unused);
+      }
+      // ---- 3. D(p) for the positions of A: compaction, then one attempt per lane per round
+      {
+        const uint32_t cnt = __popc(a16);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= static_cast<uint32_t>(d))
+            incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t at = incl - cnt;
+        uint32_t todo = a16;
+        while (todo != 0)
+        {
+          const uint32_t k = __ffs(todo) - 1;
+          todo &= todo - 1;
+          queue[at++] = static_cast<uint16_t>(lane * 16 + k);
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < total; i += 32)
+        {
+          const uint32_t off = queue[i];
+          const uint32_t res = attempt_span(t, P, T, sbase + off, bad);
+          if (res != 0)
+          {
+            dtab[off] = res;
+            atomicOr(&succ[off >> 5], 1u << (off & 31));
+          }
+        }
+        __syncwarp();
+      }
+      uint32_t succ16 = (succ[lane >> 1] >> (16 * (lane & 1))) & 0xffffu;
+      __syncwarp();
+      if (lane < 16)
+        succ[lane] = 0;
+      // ---- the window before the region: only the chain state at the region start is wanted
+      if (s < 0)
+      {
+        const uint32_t NL = __ballot_sync(0xffffffffu, cur.nl != 0);
+        if (NL != 0)
+        {
+          // fresh after the window's last newline
+          const uint32_t ln = 31u - __clz(NL);
+          const uint32_t xb = 31u - __clz(__shfl_sync(0xffffffffu, cur.nl, ln));
+          if (lane < ln)
+            succ16 = 0;
+          else if (lane == ln)
+            succ16 &= ~((2u << xb) - 1u);
+          cursor = static_cast<int64_t>(ln * 16 + xb + 1);
+        }
+        else
+        {
+          // fresh from the window's first success: to be validated against earlier regions' farthest match end
+          const uint32_t S = __ballot_sync(0xffffffffu, succ16 != 0);
+          uint64_t v = rb;
+          if (S != 0)
+          {
+            const uint32_t fl = __ffs(S) - 1;
+            v = sbase + fl * 16 + (__ffs(__shfl_sync(0xffffffffu, succ16, fl)) - 1);
+          }
+          vpoint = v;
+          cursor = 0;
+        }
+      }
+      // ---- 4. the chain over this span's successes
+      const uint32_t S = __ballot_sync(0xffffffffu, succ16 != 0);
+      uint32_t sel = 0;
+      int64_t e_out = 0;
+      uint64_t far_end = 0;
+      if (S != 0)
+      {
+        // every lane on its own, assuming the cursor is at or before its first success
+        const int32_t lbase = static_cast<int32_t>(lane * 16);
+        {
+          int32_t e = 0;
+          uint32_t m = succ16;
+          while (m != 0)
+          {
+            const int32_t k = __ffs(m) - 1;
+            m &= m - 1;
+            const int32_t p = lbase + k;
+            const int32_t end = p + static_cast<int32_t>(dtab[p] & 0xffffu);
+            if (static_cast<uint64_t>(end) > far_end)
+              far_end = end;
+            if (p >= e)
+            {
+              sel |= 1u << k;
+              e = end;
+            }
+          }
+          e_out = e;
+        }
+        // the cursor that really reaches me: the previous success lane's, or the span's
+        const uint32_t before = S & ((1u << lane) - 1u);
+        const uint32_t pl = before != 0 ? 31u - __clz(before) : lane;
+        const int64_t e_prev = __shfl_sync(0xffffffffu, e_out, pl);
+        const int64_t e_in = before != 0 ? e_prev : cursor;
+        const int32_t p1 = lbase + (__ffs(succ16) - 1);
+        const bool ok = succ16 == 0 || e_in <= p1;
+        if (!__all_sync(0xffffffffu, ok))
+        {
+          // a match straddles into some lane's first success: lane after lane from the first such lane
+          const uint32_t first_bad = __ffs(__ballot_sync(0xffffffffu, !ok)) - 1;
+          const uint32_t lower = S & ((1u << first_bad) - 1u);
+          int64_t e = lower != 0 ? __shfl_sync(0xffffffffu, e_out, 31u - __clz(lower)) : cursor;
+          uint32_t rest = S & ~((1u << first_bad) - 1u);
+          while (rest != 0)
+          {
+            const uint32_t L = __ffs(rest) - 1;
+            rest &= rest - 1;
+            if (lane == L)
+            {
+              sel = 0;
+              int64_t ee = e;
+              uint32_t m = succ16;
+              while (m != 0)
+              {
+                const int32_t k = __ffs(m) - 1;
+                m &= m - 1;
+                const int32_t p = lbase + k;
+                if (p >= ee)
+                {
+                  sel |= 1u << k;
+                  ee = p + static_cast<int32_t>(dtab[p] & 0xffffu);
+                }
+              }
+              e_out = ee;
+            }
+            e = __shfl_sync(0xffffffffu, e_out, L);
+          }
+          cursor = e;
+        }
+        else
+        {
+          const int64_t last_e = __shfl_sync(0xffffffffu, e_out, 31u - __clz(S));
+          cursor = last_e > cursor ? last_e : cursor;
+        }
+      }
+      if (s >= 0)
+      {
+        // ---- ownership: the matches that start in spans 0..31 of this region
+        const uint32_t nsel = __popc(sel);
+        if (far_end != 0)
+        {
+          const uint64_t fe = sbase + far_end;
+          if (s == SP_SPANS - 1)
+            elast = fe > elast ? fe : elast;
+          else
+            emain = fe > emain ? fe : emain;
+        }
+        if (EMIT)
+        {
+          // record index and line number of every selected match
+          uint32_t mi = nsel, ni = __popc(cur.nl);
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1)
+          {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, mi, d), z = __shfl_up_sync(0xffffffffu, ni, d);
+            if (lane >= static_cast<uint32_t>(d))
+            {
+              mi += y;
+              ni += z;
+            }
+          }
+          const uint32_t mtot = __shfl_sync(0xffffffffu, mi, 31), ntot = __shfl_sync(0xffffffffu, ni, 31);
+          uint64_t idx = out_base + m_run + (mi - nsel);
+          const uint64_t lno = line_base + nl_run + (ni - __popc(cur.nl));
+          uint32_t m = sel;
+          while (m != 0)
+          {
+            const uint32_t k = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t d = dtab[lane * 16 + k];
+            ugx_match rec;
+            rec.line = lno + __popc(cur.nl & ((1u << k) - 1u));
+            rec.offset = sbase + lane * 16 + k + a.base_offset;
+            rec.len = d & 0xffffu;
+            rec.cap = d >> 16;
+            if (idx < a.out_cap)
+              a.out[idx] = rec;
+            ++idx;
+          }
+          m_run += mtot;
+          nl_run += ntot;
+        }
+        else
+        {
+          m_run += nsel;            // lane-private here; reduced after the region
+          nl_run += __popc(cur.nl);
+        }
+      }
+      __syncwarp(); // dtab / queue are rewritten by the next span
+      cursor -= SP_SPAN;
+      cur = nxt;
+    }
+    if (!EMIT)
+    {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1)
+      {
+        m_run += __shfl_down_sync(0xffffffffu, m_run, d);
+        nl_run += __shfl_down_sync(0xffffffffu, nl_run, d);
+        const uint64_t x = __shfl_down_sync(0xffffffffu, emain, d), y = __shfl_down_sync(0xffffffffu, elast, d);
+        emain = x > emain ? x : emain;
+        elast = y > elast ? y : elast;
+      }
+      if (lane == 0)
+      {
+        a.reg_matches[r] = m_run;
+        a.reg_newlines[r] = nl_run;
+        a.reg_emain[r] = emain;
+        a.reg_elast[r] = elast;
+        a.reg_v[r] = vpoint;
+      }
+    }
+  }
+  if (bad != 0)
+    atomicOr(a.flags, bad);
+}
+
+// one CTA: exclusive prefixes of the regions' match / newline counts, the validation of the regions' chain starts,
+// and the buffer's last line (line-at-a-time form, one thread).
+// totals: [0] matches, [1] newlines, [2] fallback flag (1 = the spans' result is not valid), [3] matches before the
+// last line, [4] newlines before the last line
+template <bool EMIT>
+__global__ void __launch_bounds__(512)
+span_final_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, SpanArgs a,
+                  unsigned long long* __restrict__ totals)
+{
+  __shared__ uint64_t sm[512], sn[512];
+  __shared__ uint64_t s_body[512];      // farthest match end over a thread's regions except its last one
+  __shared__ uint64_t s_last_full[512]; // max(emain, elast) of the thread's last region
+  __shared__ uint64_t s_last_main[512]; // emain of the thread's last region
+  __shared__ uint64_t s_before[512];    // farthest match end over all regions of the threads before
+  __shared__ uint32_t s_viol;
+  const uint64_t limit = a.tail[0];
+  const uint64_t nreg = (limit + SC_REGION - 1) / SC_REGION;
+  if (!EMIT)
+  {
+    if (threadIdx.x == 0)
+      s_viol = 0;
+    const uint64_t per = (nreg + blockDim.x - 1) / blockDim.x;
+    const uint64_t lo = threadIdx.x * per < nreg ? threadIdx.x * per : nreg;
+    const uint64_t hi = lo + per < nreg ? lo + per : nreg;
+    uint64_t x = 0, y = 0, body = 0, lfull = 0, lmain = 0;
+    for (uint64_t i = lo; i < hi; ++i)
+    {
+      x += a.reg_matches[i];
+      y += a.reg_newlines[i];
+      const uint64_t em = a.reg_emain[i], el = a.reg_elast[i];
+      const uint64_t f = em > el ? em : el;
+      if (i + 1 < hi)
+        body = f > body ? f : body;
+      else
+      {
+        lfull = f;
+        lmain = em;
+      }
+    }
+    sm[threadIdx.x] = x;
+    sn[threadIdx.x] = y;
+    s_body[threadIdx.x] = body;
+    s_last_full[threadIdx.x] = lfull;
+    s_last_main[threadIdx.x] = lmain;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      uint64_t rx = 0, ry = 0, re = 0;
+      for (uint32_t i = 0; i < blockDim.x; ++i)
+      {
+        const uint64_t px = sm[i], py = sn[i];
+        sm[i] = rx;
+        sn[i] = ry;
+        s_before[i] = re;
+        rx += px;
+        ry += py;
+        re = s_body[i] > re ? s_body[i] : re;
+        re = s_last_full[i] > re ? s_last_full[i] : re;
+      }
+      totals[3] = rx;
+      totals[4] = ry;
+    }
+    __syncthreads();
+    // Region i's chain start is valid when no success that starts before its window ends after its validation point:
+    // far2 = the farthest end over regions <= i - 2 (window and all), prev_main = over spans 0..30 of region i - 1.
+    uint64_t px = sm[threadIdx.x], py = sn[threadIdx.x];
+    uint64_t far2 = 0, prev_main = 0, prev_full = 0;
+    if (threadIdx.x > 0 && lo < hi)
+    {
+      // region lo - 1 is the last region of the thread before me (threads own `per` consecutive regions each)
+      const uint64_t bb = s_before[threadIdx.x - 1], bd = s_body[threadIdx.x - 1];
+      far2 = bb > bd ? bb : bd;
+      prev_main = s_last_main[threadIdx.x - 1];
+      prev_full = s_last_full[threadIdx.x - 1];
+    }
+    bool viol = false;
+    for (uint64_t i = lo; i < hi; ++i)
+    {
+      const uint64_t v = a.reg_v[i];
+      const uint64_t before = far2 > prev_main ? far2 : prev_main;
+      if (v != SP_NO_V && before > v)
+        viol = true;
+      const uint64_t cm = a.reg_matches[i], cn = a.reg_newlines[i];
+      const uint64_t em = a.reg_emain[i], el = a.reg_elast[i];
+      a.reg_matches[i] = px;
+      a.reg_newlines[i] = py;
+      px += cm;
+      py += cn;
+      far2 = prev_full > far2 ? prev_full : far2;
+      prev_main = em;
+      prev_full = em > el ? em : el;
+    }
+    if (viol)
+      atomicOr(&s_viol, 1u);
+    __syncthreads();
+  }
+  // ---- the last line: Matcher::match(FIND) again and again from its start (find_in_line)
+  if (threadIdx.x == 0)
+  {
+    Tables T;
+    T.cls = P.cls;
+    T.next = P.next;
+    T.pred = P.pred;
+    T.tap = P.tap;
+    const Text t{buf, n};
+    uint64_t tail_matches = 0;
+    const uint64_t before = totals[3];
+    if (limit < n)
+    {
+      const uint64_t last = n - 1;
+      const uint64_t lno = totals[4] + 1 + a.base_line;
+      const CandMap cm{nullptr, 0, 0};
+      Cursor m;
+      set_current(t, m, limit);
+      for (;;)
+      {
+        const uint32_t cap = find_in_line<false>(t, P, T, cm, m, last);
+        if (cap == 0)
+          break;
+        if (EMIT)
+        {
+          ugx_match rec;
+          rec.line = lno;
+          rec.offset = m.txt + a.base_offset;
+          rec.len = m.len;
+          rec.cap = cap;
+          if (before + tail_matches < a.out_cap)
+            a.out[before + tail_matches] = rec;
+        }
+        ++tail_matches;
+      }
+    }
+    if (!EMIT)
+    {
+      totals[0] = before + tail_matches;
+      totals[1] = totals[4] + ((limit < n && buf[n - 1] == '\n') ? 1 : 0);
+      totals[2] = (s_viol != 0 || (*a.flags) != 0) ? 1 : 0;
+    }
+  }
+}
+
+// ---- host side ----
+
+bool span_scan_eligible(const DevPattern& P)
+{
+  return P.has_meta == 0 && (P.flags & UGX_OPT_W) == 0 && P.acc0 == 0 && P.adv != UGX_ADV_NONE &&
+         (P.lbk == 0 || P.lbk == 0xffff);
+}
+
+static int span_threads(const DevPattern& P)
+{
+  if (P.table_bytes <= 24 * 1024)
+    return 256;
+  if (P.table_bytes <= 110 * 1024)
+    return 1024;
+  if (P.table_bytes <= 160 * 1024)
+    return 512;
+  return 256; // the table stays in global memory / L2
+}
+
+static size_t span_smem_bytes(const DevPattern& P, bool stage, int threads)
+{
+  return 256 + UGX_HASH + UGX_BTAP + 256 + static_cast<size_t>(threads / 32) * (SP_SPAN * 4 + 64 + SP_SPAN * 2) +
+         (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
+}
+
+template <bool EMIT, int THREADS>
+static cudaError_t launch_span_one(const DevPattern& P, const uint8_t* buf, uint64_t n, SpanArgs a, size_t smem, int sm_count,
+                                   cudaStream_t st)
+{
+  auto kern = span_scan_kernel<EMIT, THREADS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, UGX_MAX_DYN_SMEM);
+  if (e != cudaSuccess)
+    return e;
+  int per_sm = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
+  if (e != cudaSuccess)
+    return e;
+  if (per_sm < 1)
+    per_sm = 1;
+  uint64_t g = static_cast<uint64_t>(sm_count) * per_sm;
+  const uint64_t need = ((n + SC_REGION - 1) / SC_REGION + THREADS / 32 - 1) / (THREADS / 32);
+  if (g > need)
+    g = need;
+  if (g == 0)
+    g = 1;
+  kern<<<static_cast<int>(g), THREADS, smem, st>>>(P, buf, n, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_last_line(const uint8_t* buf, uint64_t n, uint64_t* tail, cudaStream_t st)
+{
+  last_line_kernel<<<1, 32, 0, st>>>(buf, n, tail);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_span_scan(const DevPattern& P, const uint8_t* buf, uint64_t n, SpanArgs a, bool emit, int sm_count,
+                             cudaStream_t st)
+{
+  const int threads = span_threads(P);
+  const bool stage = P.table_bytes <= 160 * 1024 && span_smem_bytes(P, true, threads) <= static_cast<size_t>(UGX_MAX_DYN_SMEM);
+  const size_t smem = span_smem_bytes(P, stage, threads);
+  a.stage_table = stage ? 1u : 0u;
+#define UGX_SPAN_GO(EMITF)                                                        \
+  do                                                                              \
+  {                                                                               \
+    if (threads == 1024)                                                          \
+      return launch_span_one<EMITF, 1024>(P, buf, n, a, smem, sm_count, st);      \
+    if (threads == 512)                                                           \
+      return launch_span_one<EMITF, 512>(P, buf, n, a, smem, sm_count, st);       \
+    return launch_span_one<EMITF, 256>(P, buf, n, a, smem, sm_count, st);         \
+  } while (0)
+  if (emit)
+    UGX_SPAN_GO(true);
+  UGX_SPAN_GO(false);
+#undef UGX_SPAN_GO
+}
+
+cudaError_t launch_span_final(const DevPattern& P, const uint8_t* buf, uint64_t n, const SpanArgs& a, bool emit,
+                              unsigned long long* totals, cudaStream_t st)
+{
+  if (emit)
+    span_final_kernel<true><<<1, 512, 0, st>>>(P, buf, n, a, totals);
+  else
+    span_final_kernel<false><<<1, 512, 0, st>>>(P, buf, n, a, totals);
+  return cudaGetLastError();
+}
+
+} // namespace ugx
