@@ -87,3 +87,68 @@ def test_chain_over_attempt_set_equals_find(name):
         want = op.find_all(data)
         got = _model(op, f, data)
         assert [(int(r["offset"]), int(r["len"]), int(r["cap"])) for r in want] == got, (name, case["input"])
+
+
+# ---- the k-gram viability table (csrc/pattern_host.cpp build_viability): a position it rejects never starts a match
+
+def _viability(path):
+    import ctypes as C
+    from ugrep_b200 import api
+    L = api.lib()
+    raw = open(path, "rb").read()
+    nop = struct.unpack_from("<I", raw, 8)[0]
+    pre = 24 + 48 + 256 + 256 + 2048 + 4096 + 4096 + 32 + 32 + 256
+    opc = (C.c_uint32 * nop).from_buffer_copy(raw[pre:pre + 4 * nop])
+    k = C.c_uint32()
+    n = (C.c_uint32 * 4)()
+    ids = (C.c_uint32 * 256)()
+    pair = (C.c_uint8 * 16384)()
+    bits = (C.c_uint32 * 8192)()
+    npair, words = C.c_uint32(), C.c_uint32()
+    L.ugx_viability_describe.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    rc = L.ugx_viability_describe(opc, nop, C.byref(k), n, ids, pair, 16384, C.byref(npair), bits, 8192, C.byref(words))
+    assert rc == 0
+    return (k.value, list(n), np.frombuffer(ids, dtype=np.uint32).copy(),
+            np.frombuffer(pair, dtype=np.uint8)[:npair.value].copy(), np.frombuffer(bits, dtype=np.uint32)[:words.value].copy())
+
+
+def _viable_mask(v, a):
+    """the device's test (span_scan.cu viable16) for positions 0 .. len(a) - 4"""
+    k, n, ids, pair, bits = v
+    m = len(a) - 3
+    i0 = (ids[a[0:m]] & 0xff).astype(np.int64)
+    i1 = ((ids[a[1:m + 1]] >> 8) & 0xff).astype(np.int64)
+    i2 = ((ids[a[2:m + 2]] >> 16) & 0xff).astype(np.int64)
+    i3 = ((ids[a[3:m + 3]] >> 24) & 0xff).astype(np.int64)
+    code = pair[i0 * n[1] + i1].astype(np.int64)
+    idx = (np.where(code == 255, 0, code) * n[2] + i2) * n[3] + i3
+    bit = ((bits[idx >> 5] >> (idx & 31).astype(np.uint32)) & 1).astype(bool)
+    return (code == 255) | ((code != 0) & bit)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_viability_never_rejects_a_match_start(name):
+    path = G.pattern_path(name)
+    op = O.OraclePattern(path)
+    v = _viability(path)
+    assert v[0] in (0, 2, 3, 4)
+    if v[0] == 0:
+        return
+    for case, data in G.cases(name):
+        a = np.frombuffer(data[:30000], dtype=np.uint8)
+        if len(a) < 8:
+            continue
+        viable = _viable_mask(v, a)
+        for p in np.flatnonzero(~viable)[:4000]:
+            cap, ln = op.match_at(a, int(p))
+            assert not (cap and ln), (name, case["input"], int(p))
+
+
+def test_viability_is_selective_on_the_configs():
+    """the table is worth its lookups: on the c5 corpus it spares most of the attempt set (a third of all positions)"""
+    import os
+    from ugrep_b200 import corpus
+    v = _viability(os.path.join(O.ROOT, "ugrep_b200", "patterns", "c5.ugxp"))
+    assert v[0] == 4
+    assert _viable_mask(v, corpus.block("c5", 100000)).mean() < 0.08

@@ -237,6 +237,18 @@ static int pattern_create_impl(const uint32_t* opc, uint32_t nop, const ugx_pref
   opcp.push_back(ugx::OP_HALT);
   std::vector<uint16_t> next = p->dfa.next;
   next.resize((next.size() + 7) / 8 * 8, ugx::DEAD); // whole uint4s for the staging loop
+  ugx::Viability via;
+  ugx::build_viability(p->dfa, via);
+  d.via_k = via.k;
+  for (int i = 0; i < 4; ++i)
+    d.via_n[i] = via.n[i];
+  via.bits.resize((via.bits.size() + 3) / 4 * 4 + 4, 0); // whole uint4s for the staging copy
+  via.pair.resize((via.pair.size() + 15) / 16 * 16 + 16, 0);
+  d.via_words = static_cast<uint32_t>(via.bits.size());
+  d.via_pair_bytes = static_cast<uint32_t>(via.pair.size());
+  uint32_t* d_vids = nullptr;
+  uint32_t* d_vbits = nullptr;
+  uint8_t* d_vpair = nullptr;
   uint8_t* d_cls = nullptr;
   uint16_t* d_next = nullptr;
   uint32_t* d_acc = nullptr;
@@ -251,7 +263,10 @@ static int pattern_create_impl(const uint32_t* opc, uint32_t nop, const ugx_pref
   if (rc == UGX_OK) { p->allocs.push_back(d_opc); rc = upload(d_pred, pf->min < 4 ? pf->pma : pf->pmh, UGX_HASH); }
   if (rc == UGX_OK) { p->allocs.push_back(d_pred); rc = upload(d_tap, pf->tap, UGX_BTAP); }
   if (rc == UGX_OK) { p->allocs.push_back(d_tap); rc = upload(d_words, k_word_ranges, sizeof(k_word_ranges)); }
-  if (rc == UGX_OK) p->allocs.push_back(d_words);
+  if (rc == UGX_OK) { p->allocs.push_back(d_words); rc = upload(d_vids, via.ids, sizeof(via.ids)); }
+  if (rc == UGX_OK) { p->allocs.push_back(d_vids); rc = upload(d_vbits, via.bits.data(), via.bits.size() * 4); }
+  if (rc == UGX_OK) { p->allocs.push_back(d_vbits); rc = upload(d_vpair, via.pair.data(), via.pair.size()); }
+  if (rc == UGX_OK) p->allocs.push_back(d_vpair);
   if (rc != UGX_OK)
   {
     return rc;
@@ -263,6 +278,9 @@ static int pattern_create_impl(const uint32_t* opc, uint32_t nop, const ugx_pref
   d.pred = d_pred;
   d.tap = d_tap;
   d.word_ranges = d_words;
+  d.via_ids = d_vids;
+  d.via_bits = d_vbits;
+  d.via_pair = d_vpair;
   *out = holder.release();
   return UGX_OK;
 }
@@ -325,6 +343,39 @@ static int plan_describe_impl(const uint32_t* opc, uint32_t nop, const ugx_prefi
   if (rc != UGX_OK)
     return fail(rc, err);
   return UGX_OK;
+}
+
+int ugx_viability_describe(const uint32_t* opc, uint32_t nop, uint32_t* k, uint32_t* n, uint32_t* ids, uint8_t* pair,
+                           uint32_t cap_pair, uint32_t* npair, uint32_t* bits, uint32_t cap_words, uint32_t* words)
+{
+  if (opc == nullptr || nop == 0 || k == nullptr || n == nullptr || ids == nullptr || npair == nullptr || words == nullptr)
+    return fail(UGX_E_INVALID, "ugx_viability_describe: null argument");
+  try
+  {
+    ugx::HostDfa dfa;
+    std::string err;
+    const int rc = ugx::flatten_dfa(opc, nop, dfa, err);
+    if (rc != UGX_OK)
+      return fail(rc, err);
+    ugx::Viability v;
+    ugx::build_viability(dfa, v);
+    *k = v.k;
+    memcpy(n, v.n, sizeof(v.n));
+    memcpy(ids, v.ids, sizeof(v.ids));
+    *npair = static_cast<uint32_t>(v.pair.size());
+    *words = static_cast<uint32_t>(v.bits.size());
+    if (v.bits.size() > cap_words || v.pair.size() > cap_pair)
+      return fail(UGX_E_OVERFLOW, "viability table larger than the caller's buffer");
+    if (!v.pair.empty() && pair != nullptr)
+      memcpy(pair, v.pair.data(), v.pair.size());
+    if (!v.bits.empty() && bits != nullptr)
+      memcpy(bits, v.bits.data(), v.bits.size() * 4);
+    return UGX_OK;
+  }
+  catch (const std::exception&)
+  {
+    return fail(UGX_E_NOMEM, "out of host memory");
+  }
 }
 
 int ugx_pattern_load(const char* path, int device, ugx_pattern** out)

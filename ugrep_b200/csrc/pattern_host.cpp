@@ -341,6 +341,156 @@ int flatten_dfa(const uint32_t* opc, uint32_t nop, HostDfa& out, std::string& er
   return UGX_OK;
 }
 
+// ---- k-gram viability ----------------------------------------------------------------------------------
+
+void build_viability(const HostDfa& dfa, Viability& v, uint32_t max_bits)
+{
+  v = Viability();
+  if (dfa.has_meta || dfa.nstates == 0 || dfa.accept[0] != 0)
+    return;
+  const uint32_t ncls = dfa.ncls;
+  auto step = [&](uint32_t s, uint32_t b) -> uint16_t { return dfa.next[static_cast<size_t>(s) * ncls + dfa.cls[b]]; };
+  // ids of a level: bytes that every state of `level` treats alike share an id; returns false when there are too many
+  auto assign_ids = [&](const std::vector<uint32_t>& level, uint32_t shift, std::vector<uint8_t>& reps) -> bool {
+    std::map<std::vector<uint16_t>, uint32_t> id_of;
+    uint32_t ids[256];
+    reps.clear();
+    for (uint32_t b = 0; b < 256; ++b)
+    {
+      std::vector<uint16_t> col(level.size());
+      for (size_t j = 0; j < level.size(); ++j)
+        col[j] = step(level[j], b);
+      auto it = id_of.find(col);
+      if (it == id_of.end())
+      {
+        it = id_of.emplace(col, static_cast<uint32_t>(reps.size())).first;
+        reps.push_back(static_cast<uint8_t>(b));
+      }
+      ids[b] = it->second;
+    }
+    if (reps.size() > 255)
+      return false;
+    for (uint32_t b = 0; b < 256; ++b)
+      v.ids[b] |= ids[b] << shift;
+    return true;
+  };
+  auto targets = [&](const std::vector<uint32_t>& level) {
+    std::vector<uint8_t> seen(dfa.nstates, 0);
+    std::vector<uint32_t> out;
+    for (uint32_t s : level)
+      for (uint32_t c = 0; c < ncls; ++c)
+      {
+        const uint16_t t = dfa.next[static_cast<size_t>(s) * ncls + c];
+        if (t != DEAD && !seen[t])
+        {
+          seen[t] = 1;
+          out.push_back(t);
+        }
+      }
+    return out;
+  };
+  // ---- first two bytes: pair table
+  std::vector<uint8_t> rep0, rep1;
+  const std::vector<uint32_t> l0{0u};
+  if (!assign_ids(l0, 0, rep0))
+    return;
+  const std::vector<uint32_t> l1 = targets(l0);
+  if (l1.empty() || !assign_ids(l1, 8, rep1) || rep0.size() * rep1.size() > 16384)
+  {
+    memset(v.ids, 0, sizeof(v.ids));
+    return;
+  }
+  v.n[0] = static_cast<uint32_t>(rep0.size());
+  v.n[1] = static_cast<uint32_t>(rep1.size());
+  v.pair.assign(static_cast<size_t>(v.n[0]) * v.n[1], 0);
+  std::vector<uint32_t> s2; // distinct live states after two bytes
+  std::map<uint32_t, uint32_t> s2_id;
+  bool overflow = false;
+  for (uint32_t a = 0; a < v.n[0]; ++a)
+    for (uint32_t b = 0; b < v.n[1]; ++b)
+    {
+      uint8_t code = 0;
+      const uint16_t t1 = step(0, rep0[a]);
+      if (t1 != DEAD)
+      {
+        if (dfa.accept[t1] != 0)
+          code = VIA_ACCEPTED;
+        else
+        {
+          const uint16_t t2 = step(t1, rep1[b]);
+          if (t2 != DEAD)
+          {
+            if (dfa.accept[t2] != 0)
+              code = VIA_ACCEPTED;
+            else
+            {
+              auto it = s2_id.find(t2);
+              if (it == s2_id.end())
+              {
+                it = s2_id.emplace(t2, static_cast<uint32_t>(s2.size())).first;
+                s2.push_back(t2);
+              }
+              if (it->second + 1 >= VIA_ACCEPTED)
+                overflow = true;
+              code = static_cast<uint8_t>(it->second + 1);
+            }
+          }
+        }
+      }
+      v.pair[static_cast<size_t>(a) * v.n[1] + b] = code;
+    }
+  v.k = 2;
+  if (overflow)
+  {
+    // too many states after two bytes for one byte of code: every live pair just stays viable
+    for (auto& c : v.pair)
+      c = c != 0 ? VIA_ACCEPTED : 0;
+    s2.clear();
+  }
+  // ---- bytes three and four: bit table over (state code, id2, id3)
+  std::vector<uint8_t> rep2, rep3;
+  std::vector<uint32_t> l3;
+  const uint32_t saved_ids_mask = 0x0000ffffu;
+  if (!s2.empty() && assign_ids(s2, 16, rep2) && static_cast<uint64_t>(s2.size() + 1) * rep2.size() <= max_bits)
+  {
+    v.k = 3;
+    v.n[2] = static_cast<uint32_t>(rep2.size());
+    l3 = targets(s2);
+    if (!l3.empty() && assign_ids(l3, 24, rep3) && static_cast<uint64_t>(s2.size() + 1) * rep2.size() * rep3.size() <= max_bits)
+    {
+      v.k = 4;
+      v.n[3] = static_cast<uint32_t>(rep3.size());
+    }
+    else
+      for (uint32_t b = 0; b < 256; ++b)
+        v.ids[b] &= 0x00ffffffu;
+  }
+  else
+    for (uint32_t b = 0; b < 256; ++b)
+      v.ids[b] &= saved_ids_mask;
+  const uint64_t total = static_cast<uint64_t>(s2.size() + 1) * v.n[2] * v.n[3];
+  v.bits.assign((total + 31) / 32, 0);
+  for (uint32_t code = 1; code <= s2.size(); ++code)
+    for (uint32_t c2 = 0; c2 < v.n[2]; ++c2)
+      for (uint32_t c3 = 0; c3 < v.n[3]; ++c3)
+      {
+        bool ok = true;
+        if (v.k >= 3)
+        {
+          const uint16_t t3 = step(s2[code - 1], rep2[c2]);
+          if (t3 == DEAD)
+            ok = false;
+          else if (dfa.accept[t3] == 0 && v.k >= 4)
+            ok = step(t3, rep3[c3]) != DEAD;
+        }
+        if (ok)
+        {
+          const uint64_t idx = (static_cast<uint64_t>(code) * v.n[2] + c2) * v.n[3] + c3;
+          v.bits[idx >> 5] |= 1u << (idx & 31);
+        }
+      }
+}
+
 // ---- first-stage filter planning -------------------------------------------------------------------
 
 namespace {

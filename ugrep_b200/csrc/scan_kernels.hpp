@@ -65,6 +65,7 @@ struct StreamArgs {
   uint32_t accumulate;            // add to totals instead of overwriting them
   uint32_t stage_table;           // set by the launcher
   uint32_t use_h4;                // set by the launcher: stage the hashed-predictor term table
+  uint32_t use_via;               // set by the launcher: stage the k-gram viability tables (viability.cuh)
 };
 
 bool count_lines_stream_eligible(const DevPattern& P);
@@ -104,6 +105,7 @@ struct SpanArgs {
   const uint64_t* tail;    // device: [0] = start of the last line (the spans scan [0, tail[0]))
   unsigned int* flags;     // device: bit 0 an attempt failed at the end of the buffer, bit 1 a match too long for the span tables
   uint32_t stage_table;    // set by the launcher
+  uint32_t use_via;        // set by the launcher: the viability tables are staged in shared memory
 };
 
 bool span_scan_eligible(const DevPattern& P);

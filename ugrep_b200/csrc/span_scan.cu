@@ -45,6 +45,7 @@
 #include "ptx.cuh"
 #include "scan_kernels.hpp"
 #include "tile_phase_a.cuh"
+#include "viability.cuh"
 
 namespace ugx {
 
@@ -57,20 +58,22 @@ constexpr uint64_t SP_NO_V = ~0ull;           // region needs no validation (its
 constexpr uint32_t SP_FAR_SPANS = 64;         // longest look-ahead over a run of look-back bytes (32 KiB)
 
 struct SpanMasks {
-  uint32_t cand, cbk, nl; // 16 bits each: bit k = byte k of the lane's chunk
+  uint32_t cand, cbk, nl, via; // 16 bits each: bit k = byte k of the lane's chunk
 };
 
 // masks of the chunk at `base` (16-byte aligned); positions at or past `limit` read as nothing
 __device__ __forceinline__ SpanMasks eval_masks(const Text& t, const DevPattern& P, const Tables& T, const uint8_t* s_flags,
-                                                uint64_t base, uint64_t limit, bool want_cbk)
+                                                const ViaTables& via, uint64_t base, uint64_t limit, bool want_cand,
+                                                bool want_cbk)
 {
   SpanMasks m;
-  m.cand = m.cbk = m.nl = 0;
+  m.cand = m.cbk = m.nl = m.via = 0;
   if (base >= limit)
     return m;
   Window W;
   const bool interior = load_window(t.b, t.end, base, W);
-  m.cand = interior ? chunk_cand_fast(W, t, P, T, base) : chunk_cand_generic(t, P, T, base);
+  if (want_cand)
+    m.cand = interior ? chunk_cand_fast(W, t, P, T, base) : chunk_cand_generic(t, P, T, base);
   m.nl = newline_mask16(W);
   if (want_cbk)
   {
@@ -78,12 +81,15 @@ __device__ __forceinline__ SpanMasks eval_masks(const Text& t, const DevPattern&
     for (int k = 0; k < 16; ++k)
       m.cbk |= static_cast<uint32_t>(s_flags[UGX_WB(W, k)] & 1u) << k;
   }
+  // positions whose next bytes cannot start a match (the last bytes of the buffer are left to the attempt)
+  m.via = (via.on && interior) ? viable16(via, W) : 0xffffu;
   if (base + 16 > limit)
   {
     const uint32_t valid = (1u << (limit - base)) - 1u;
     m.cand &= valid;
     m.cbk &= valid;
     m.nl &= valid;
+    m.via &= valid;
   }
   return m;
 }
@@ -128,50 +134,41 @@ __device__ __forceinline__ SpanCarry span_carry(const SpanMasks& m)
   return c;
 }
 
-// one anchored attempt: (accept << 16) | length, 0 = no match.  `flags`: bit 0 the attempt failed after reading up to
-// the end of the buffer, bit 1 the match does not fit 16 bits (or its accept index 15 bits)
-__device__ __forceinline__ uint32_t attempt_span(const Text& t, const DevPattern& P, const Tables& T, uint64_t pos, uint32_t& flags)
+// the candidate test at one position, for the lazy form of the attempt set (PM4 / bitap prefilters, whose masks cost
+// several table lookups per byte: they are evaluated only where a viable position asks)
+__device__ __forceinline__ bool cand_at(const Text& t, const DevPattern& P, const Tables& T, uint64_t q)
 {
-  if (P.one)
+  if (P.adv == UGX_ADV_PMA && q + 12 <= t.end)
   {
-    if (P.len >= SP_LONG)
-      flags |= 2u;
-    return (1u << 16) | P.len; // the candidate test was the exact literal (lib/matcher.cpp:71-83)
+    const uint8_t* p = t.b + q;
+    const uint32_t sh = (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p)) & 3u) * 8;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(p - (sh >> 3));
+    return pm4_x(T.pred, __funnelshift_r(__ldg(a), __ldg(a + 1), sh));
   }
-  uint32_t state = 0, best = 0;
-  uint64_t p = pos;
-  const uint32_t first_acc = P.first_acc, ncls = P.ncls;
-  for (;;)
-  {
-    if (p >= t.end)
-      break;
-    const uint32_t ch = t.raw(p++);
-    const uint32_t nxt = T.next[state * ncls + T.cls[ch]];
-    if (nxt == D_DEAD)
-      break;
-    if (nxt >= first_acc)
-    {
-      const uint32_t acc = __ldg(P.accept + nxt);
-      if ((acc & 0x7fffffffu) != 0)
-      {
-        const uint64_t len = p - pos;
-        if (len >= SP_LONG || (acc & 0x7fffffffu) >= 0x8000u)
-          flags |= 2u;
-        best = ((acc & 0x7fffu) << 16) | static_cast<uint32_t>(len & 0xffffu);
-      }
-      if (acc & 0x80000000u) // no outgoing edges: the interpreter halts here before reading
-        return best;
-    }
-    state = nxt;
-  }
-  if (best == 0 && p >= t.end)
-    flags |= 1u;
-  return best;
+  return cand(t, P, T, q);
 }
 
-struct RegionOut {
-  uint64_t matches, newlines, emain, elast, v;
-};
+// p in A?  (A(p) = cand(p) | (cbk(p) & A(p + 1)), walked forwards from p)
+__device__ __forceinline__ bool in_attempt_set(const Text& t, const DevPattern& P, const Tables& T, const uint8_t* s_flags,
+                                               uint64_t pos, uint32_t& bad)
+{
+  uint64_t q = pos;
+  for (uint32_t steps = 0;; ++steps)
+  {
+    if (q >= t.end)
+      return false;
+    if (cand_at(t, P, T, q))
+      return true;
+    if (P.lbk == 0 || (s_flags[t.raw(q)] & 1u) == 0)
+      return false;
+    if (steps >= SP_FAR_SPANS * SP_SPAN)
+    {
+      bad |= 4u; // a look-back run longer than the bound: the buffer goes to the line-at-a-time kernels
+      return false;
+    }
+    ++q;
+  }
+}
 
 } // namespace
 
@@ -230,9 +227,11 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
   uint32_t* s_dtab = reinterpret_cast<uint32_t*>(s_flags + 256);           // [NWARPS][512] (accept << 16) | length
   uint32_t* s_succ = s_dtab + NWARPS * SP_SPAN;                            // [NWARPS][16] success bits of the span
   uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_succ + NWARPS * 16);   // [NWARPS][512] attempt positions
-  uint16_t* s_next = s_queue + NWARPS * SP_SPAN;
+  uint8_t* s_via = reinterpret_cast<uint8_t*>(s_queue + NWARPS * SP_SPAN);
+  uint16_t* s_next = reinterpret_cast<uint16_t*>(s_via + (a.use_via ? via_smem_bytes(P) : 0));
   stage_tables_bulk(&s_bar, s_cls, P.cls, s_pred, P.pred, s_tap, P.tap, s_next, P.next,
                     a.stage_table ? ((P.table_bytes + 15) / 16) * 16 : 0);
+  const ViaTables via = via_stage(P, s_via, a.use_via != 0);
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
     s_flags[i] = bit256(P.cbk, i) ? 1u : 0u;
   for (uint32_t i = threadIdx.x; i < NWARPS * 16; i += blockDim.x)
@@ -249,6 +248,11 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
   uint32_t* succ = s_succ + wid * 16;
   uint16_t* queue = s_queue + wid * SP_SPAN;
   const bool has_lb = P.lbk != 0;
+  // lazy attempt set: the prefilter's masks cost table lookups per byte (PM4 at every byte, bitap), and the viability
+  // table is there to name the few positions worth asking about — membership in A is then decided per viable position
+  const bool lazy = via.on && (P.adv == UGX_ADV_PMA || P.adv == UGX_ADV_MIN1 || P.adv == UGX_ADV_MIN2 ||
+                               P.adv == UGX_ADV_MIN3 || P.adv == UGX_ADV_MIN4);
+  const bool mask_lb = has_lb && !lazy;
   const uint64_t limit = __ldcg(a.tail); // spans own [0, limit): the last line belongs to the final kernel
   const uint64_t nregions = (limit + SC_REGION - 1) / SC_REGION;
   const uint64_t total_warps = static_cast<uint64_t>(gridDim.x) * NWARPS;
@@ -271,17 +275,17 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
     }
     // masks of the first span to process (the window before the region, or span 0 of region 0) and of the one after
     int s = r == 0 ? 0 : -1;
-    SpanMasks cur = eval_masks(t, P, T, s_flags, rb + static_cast<int64_t>(s) * SP_SPAN + lane * 16, limit, has_lb);
+    SpanMasks cur = eval_masks(t, P, T, s_flags, via, rb + static_cast<int64_t>(s) * SP_SPAN + lane * 16, limit, !lazy, mask_lb);
     for (; s < SP_SPANS; ++s)
     {
       const uint64_t sbase = rb + static_cast<int64_t>(s) * SP_SPAN;
       if (sbase >= limit)
         break;
       // ---- 1. masks of the next span (needed now for the carry into this one; they become `cur` afterwards)
-      const SpanMasks nxt = eval_masks(t, P, T, s_flags, sbase + SP_SPAN + lane * 16, limit, has_lb);
-      // ---- 2. the attempt set of this span
-      uint32_t a16 = cur.cand;
-      if (has_lb)
+      const SpanMasks nxt = eval_masks(t, P, T, s_flags, via, sbase + SP_SPAN + lane * 16, limit, !lazy, mask_lb);
+      // ---- 2. the attempt set of this span (lazy form: the viable positions, membership decided in step 3)
+      uint32_t a16 = lazy ? cur.via : cur.cand;
+      if (mask_lb)
       {
         const SpanCarry cn = span_carry(nxt);
         uint32_t cin_span = cn.out(0);
@@ -302,7 +306,7 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
                 bad |= 4u;
                 break;
               }
-              const SpanMasks far = eval_masks(t, P, T, s_flags, fb + lane * 16, limit, true);
+              const SpanMasks far = eval_masks(t, P, T, s_flags, via, fb + lane * 16, limit, true, true);
               const SpanCarry cf = span_carry(far);
               const uint32_t o0 = cf.out(0);
               if (cf.out(1) == o0)
@@ -319,7 +323,11 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
         uint32_t unused;
         a16 = flood16(cur.cand, cur.cbk, cc.into(cin_span, lane), unused);
       }
-      // ---- 3. D(p) for the positions of A: compaction, then one attempt per lane per round
+      if (!lazy)
+        a16 &= cur.via; // a position that cannot start a match needs no attempt (its D is 0 either way)
+      // ---- 3. D(p) for the positions of A: compaction, then ONE loop whose body is a single DFA transition — a lane
+      // that finishes an attempt takes its next position in the same iteration, so the lanes keep stepping together
+      // whatever the lengths of their attempts
       {
         const uint32_t cnt = __popc(a16);
         uint32_t incl = cnt;
@@ -340,14 +348,70 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
           queue[at++] = static_cast<uint16_t>(lane * 16 + k);
         }
         __syncwarp();
-        for (uint32_t i = lane; i < total; i += 32)
+        const uint8_t* __restrict__ sp = buf + sbase;
+        const uint32_t rel_end = n - sbase > 0x7fffffffull ? 0x7fffffffu : static_cast<uint32_t>(n - sbase);
+        const uint32_t first_acc = P.first_acc, ncls = P.ncls;
+        uint32_t i = lane, off = 0, pp = 0, state = 0, best = 0;
+        bool active = false;
+        for (;;)
         {
-          const uint32_t off = queue[i];
-          const uint32_t res = attempt_span(t, P, T, sbase + off, bad);
-          if (res != 0)
+          if (!active)
           {
-            dtab[off] = res;
-            atomicOr(&succ[off >> 5], 1u << (off & 31));
+            if (i >= total)
+              break;
+            off = queue[i];
+            i += 32;
+            if (lazy && !in_attempt_set(t, P, T, s_flags, sbase + off, bad))
+              continue;
+            if (P.one)
+            {
+              // the candidate test was the exact literal (lib/matcher.cpp:71-83)
+              if (P.len >= SP_LONG)
+                bad |= 2u;
+              dtab[off] = (1u << 16) | P.len;
+              atomicOr(&succ[off >> 5], 1u << (off & 31));
+              continue;
+            }
+            pp = off;
+            state = 0;
+            best = 0;
+            active = true;
+          }
+          bool stop = pp >= rel_end;
+          if (!stop)
+          {
+            const uint32_t ch = __ldg(sp + pp);
+            ++pp;
+            const uint32_t nx = T.next[state * ncls + T.cls[ch]];
+            if (nx == D_DEAD)
+              stop = true;
+            else
+            {
+              if (nx >= first_acc)
+              {
+                const uint32_t acc = __ldg(P.accept + nx);
+                if ((acc & 0x7fffffffu) != 0)
+                {
+                  const uint32_t len = pp - off;
+                  if (len >= SP_LONG || (acc & 0x7fffffffu) >= 0x8000u)
+                    bad |= 2u;
+                  best = ((acc & 0x7fffu) << 16) | (len & 0xffffu);
+                }
+                stop = (acc & 0x80000000u) != 0; // no outgoing edges: the interpreter halts here before reading
+              }
+              state = nx;
+            }
+          }
+          if (stop)
+          {
+            if (best != 0)
+            {
+              dtab[off] = best;
+              atomicOr(&succ[off >> 5], 1u << (off & 31));
+            }
+            else if (pp >= rel_end)
+              bad |= 1u; // failed after reading up to the end of the buffer (see the file header)
+            active = false;
           }
         }
         __syncwarp();
@@ -701,10 +765,10 @@ static int span_threads(const DevPattern& P)
   return 256; // the table stays in global memory / L2
 }
 
-static size_t span_smem_bytes(const DevPattern& P, bool stage, int threads)
+static size_t span_smem_bytes(const DevPattern& P, bool stage, bool use_via, int threads)
 {
   return 256 + UGX_HASH + UGX_BTAP + 256 + static_cast<size_t>(threads / 32) * (SP_SPAN * 4 + 64 + SP_SPAN * 2) +
-         (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
+         (use_via ? via_smem_bytes(P) : 0) + (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
 }
 
 template <bool EMIT, int THREADS>
@@ -741,9 +805,13 @@ cudaError_t launch_span_scan(const DevPattern& P, const uint8_t* buf, uint64_t n
                              cudaStream_t st)
 {
   const int threads = span_threads(P);
-  const bool stage = P.table_bytes <= 160 * 1024 && span_smem_bytes(P, true, threads) <= static_cast<size_t>(UGX_MAX_DYN_SMEM);
-  const size_t smem = span_smem_bytes(P, stage, threads);
+  // the viability tables are small and spare most attempts: they get shared memory before the transition table does
+  const bool use_via = P.via_k != 0 && span_smem_bytes(P, false, true, threads) <= static_cast<size_t>(UGX_MAX_DYN_SMEM);
+  const bool stage = P.table_bytes <= 160 * 1024 &&
+                     span_smem_bytes(P, true, use_via, threads) <= static_cast<size_t>(UGX_MAX_DYN_SMEM);
+  const size_t smem = span_smem_bytes(P, stage, use_via, threads);
   a.stage_table = stage ? 1u : 0u;
+  a.use_via = use_via ? 1u : 0u;
 #define UGX_SPAN_GO(EMITF)                                                        \
   do                                                                              \
   {                                                                               \

@@ -28,6 +28,7 @@
 #include "ptx.cuh"
 #include "stream_common.cuh"
 #include "tile_phase_a.cuh"
+#include "viability.cuh"
 
 namespace ugx {
 
@@ -229,6 +230,7 @@ struct DfaEval {
   uint32_t* succ;       // [16] per warp: success bits of the span, bit (16 * lane + k)
   uint32_t nterms, off0, off1, off2;
   bool use_lut;
+  ViaTables via;        // k-gram viability of an attempt: a survivor that cannot start a match is dropped before stage 2
 
   __device__ __forceinline__ void try_at(uint64_t sbase, uint32_t off, bool exact) const
   {
@@ -326,6 +328,14 @@ struct DfaEval {
       exact = true;
       surv = exact_chunk_candidates(t, P, T, sbase + lane * 16, w[0], w[1], w[2], w[3], w[4], w[5]);
     }
+    if (via.on && interior && surv != 0)
+    {
+      Window W;
+#pragma unroll
+      for (int i = 0; i < 7; ++i)
+        W.w[i] = w[i];
+      surv &= viable16(via, W);
+    }
     if (!__any_sync(0xffffffffu, surv != 0))
       return false;
     // ---- compaction + balanced stage 2.  Per round: a warp scan of the lanes' survivor counts; the lanes whose
@@ -399,11 +409,13 @@ count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* _
   uint32_t* s_succ = s_lut + 256;
   uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_succ + 16 * NWARPS);
   uint32_t* s_h4 = reinterpret_cast<uint32_t*>(s_queue + 64 * NWARPS);
-  uint16_t* s_next = reinterpret_cast<uint16_t*>(s_h4 + (a.use_h4 ? UGX_HASH : 0));
+  uint8_t* s_via = reinterpret_cast<uint8_t*>(s_h4 + (a.use_h4 ? UGX_HASH : 0));
+  uint16_t* s_next = reinterpret_cast<uint16_t*>(s_via + (a.use_via ? via_smem_bytes(P) : 0));
   // ---- tables -> shared memory by bulk asynchronous copies (cp.async.bulk, the TMA path without a tensor map)
   __shared__ __align__(8) uint64_t s_bar;
   stage_tables_bulk(&s_bar, s_cls, P.cls, s_pred, P.pred, s_tap, P.tap, s_next, P.next,
                     a.stage_table ? ((P.table_bytes + 15) / 16) * 16 : 0);
+  const ViaTables via = via_stage(P, s_via, a.use_via != 0 && KIND == SK_TABLE);
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
     s_lut[i] = P.plan.pm2 ? (((__ldg(P.pred + i) >> 7) & 1u) | (((__ldg(P.pred + i) >> 6) & 1u) << 8)) : P.plan.lut[i];
   for (uint32_t i = threadIdx.x; i < 16 * NWARPS; i += blockDim.x)
@@ -432,16 +444,18 @@ count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* _
                    P.plan.pm2 != 0 && a.use_h4 != 0,
                    s_queue + 64 * wid, s_succ + 16 * wid,
                    P.plan.nterms, P.plan.t_off[0], P.plan.t_off[1], P.plan.t_off[2],
-                   P.plan.kind == FK_LUT && P.plan.nterms >= 1};
+                   P.plan.kind == FK_LUT && P.plan.nterms >= 1, via};
   stream_scan<WANT_NL, false, 1>(buf, n, a, ev);
 }
 
 static bool stream_use_h4(const DevPattern& P) { return P.plan.h4_terms >= 1 || P.plan.pm2 != 0; }
 
+static bool stream_use_via(const DevPattern& P) { return P.via_k != 0 && P.has_meta == 0 && P.one == 0 && via_smem_bytes(P) <= 40 * 1024; }
+
 static size_t stream_smem_bytes(const DevPattern& P, bool stage, int threads)
 {
   return 256 + UGX_HASH + UGX_BTAP + 1024 + (threads / 32) * (64 + 128) + (stream_use_h4(P) ? 4 * UGX_HASH : 0) +
-         (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
+         (stream_use_via(P) ? via_smem_bytes(P) : 0) + (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
 }
 
 bool count_lines_stream_eligible(const DevPattern& P)
@@ -495,6 +509,7 @@ cudaError_t launch_count_lines_stream(const DevPattern& P, const uint8_t* buf, u
   const size_t smem = stream_smem_bytes(P, stage, big ? 1024 : 256);
   a.stage_table = stage ? 1u : 0u;
   a.use_h4 = stream_use_h4(P) ? 1u : 0u;
+  a.use_via = stream_use_via(P) ? 1u : 0u;
   if (meta)
     return want_nl ? launch_dfa<SK_META, true, 256>(P, buf, n, a, smem, sm_count, st)
                    : launch_dfa<SK_META, false, 256>(P, buf, n, a, smem, sm_count, st);
