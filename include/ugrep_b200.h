@@ -165,10 +165,10 @@ int  ugx_pattern_load(const char *path, int device, ugx_pattern **out);
 /* host only (no device needed): DFA export + filter plan of a compiled pattern */
 int  ugx_plan_describe(const uint32_t *opc, uint32_t nop, const ugx_prefilter *pf, uint32_t matcher_flags,
                        ugx_plan_info *out);
-/* host only: the k-gram viability table of the span kernels (csrc/pattern_host.hpp).  *k = bytes looked at (0 = no
- * table), n[4] = ids per level, ids[256] = packed per-level byte ids, pair[cap_pair] = the two-byte state codes,
- * bits[cap_words] = the table of bytes three and four; *npair / *words = their sizes */
-int  ugx_viability_describe(const uint32_t *opc, uint32_t nop, uint32_t *k, uint32_t *n, uint32_t *ids,
+/* host only: the k-gram viability tables of the scan kernels (csrc/pattern_host.hpp).  *k = bytes looked at (0 = no
+ * table), *stride = bits per state code, t01[256] / t23[256] = the pre-multiplied byte ids, pair[cap_pair] = the
+ * two-byte state codes, bits[cap_words] = the bit table; *npair / *words = their sizes */
+int  ugx_viability_describe(const uint32_t *opc, uint32_t nop, uint32_t *k, uint32_t *stride, uint32_t *t01, uint32_t *t23,
                             uint8_t *pair, uint32_t cap_pair, uint32_t *npair,
                             uint32_t *bits, uint32_t cap_words, uint32_t *words);
 int  ugx_pattern_info_get(const ugx_pattern *p, ugx_pattern_info *info);

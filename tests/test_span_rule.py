@@ -99,32 +99,28 @@ def _viability(path):
     nop = struct.unpack_from("<I", raw, 8)[0]
     pre = 24 + 48 + 256 + 256 + 2048 + 4096 + 4096 + 32 + 32 + 256
     opc = (C.c_uint32 * nop).from_buffer_copy(raw[pre:pre + 4 * nop])
-    k = C.c_uint32()
-    n = (C.c_uint32 * 4)()
-    ids = (C.c_uint32 * 256)()
+    k, stride = C.c_uint32(), C.c_uint32()
+    t01 = (C.c_uint32 * 256)()
+    t23 = (C.c_uint32 * 256)()
     pair = (C.c_uint8 * 16384)()
     bits = (C.c_uint32 * 8192)()
     npair, words = C.c_uint32(), C.c_uint32()
-    L.ugx_viability_describe.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+    L.ugx_viability_describe.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
-    rc = L.ugx_viability_describe(opc, nop, C.byref(k), n, ids, pair, 16384, C.byref(npair), bits, 8192, C.byref(words))
+    rc = L.ugx_viability_describe(opc, nop, C.byref(k), C.byref(stride), t01, t23, pair, 16384, C.byref(npair), bits, 8192,
+                                  C.byref(words))
     assert rc == 0
-    return (k.value, list(n), np.frombuffer(ids, dtype=np.uint32).copy(),
+    return (k.value, stride.value, np.frombuffer(t01, dtype=np.uint32).copy(), np.frombuffer(t23, dtype=np.uint32).copy(),
             np.frombuffer(pair, dtype=np.uint8)[:npair.value].copy(), np.frombuffer(bits, dtype=np.uint32)[:words.value].copy())
 
 
 def _viable_mask(v, a):
-    """the device's test (span_scan.cu viable16) for positions 0 .. len(a) - 4"""
-    k, n, ids, pair, bits = v
+    """the device's test (csrc/viability.cuh viable16) for positions 0 .. len(a) - 4"""
+    k, stride, t01, t23, pair, bits = v
     m = len(a) - 3
-    i0 = (ids[a[0:m]] & 0xff).astype(np.int64)
-    i1 = ((ids[a[1:m + 1]] >> 8) & 0xff).astype(np.int64)
-    i2 = ((ids[a[2:m + 2]] >> 16) & 0xff).astype(np.int64)
-    i3 = ((ids[a[3:m + 3]] >> 24) & 0xff).astype(np.int64)
-    code = pair[i0 * n[1] + i1].astype(np.int64)
-    idx = (np.where(code == 255, 0, code) * n[2] + i2) * n[3] + i3
-    bit = ((bits[idx >> 5] >> (idx & 31).astype(np.uint32)) & 1).astype(bool)
-    return (code == 255) | ((code != 0) & bit)
+    code = pair[(t01[a[0:m]] & 0xffff).astype(np.int64) + (t01[a[1:m + 1]] >> 16)].astype(np.int64)
+    idx = code * stride + (t23[a[2:m + 2]] & 0xffff) + (t23[a[3:m + 3]] >> 16)
+    return ((bits[idx >> 5] >> (idx & 31).astype(np.uint32)) & 1).astype(bool)
 
 
 @pytest.mark.parametrize("name", NAMES)

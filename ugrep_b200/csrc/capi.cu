@@ -240,8 +240,13 @@ static int pattern_create_impl(const uint32_t* opc, uint32_t nop, const ugx_pref
   ugx::Viability via;
   ugx::build_viability(p->dfa, via);
   d.via_k = via.k;
-  for (int i = 0; i < 4; ++i)
-    d.via_n[i] = via.n[i];
+  d.via_stride = via.stride;
+  std::vector<uint32_t> via_t(512);
+  for (int b = 0; b < 256; ++b)
+  {
+    via_t[2 * b] = via.t01[b];
+    via_t[2 * b + 1] = via.t23[b];
+  }
   via.bits.resize((via.bits.size() + 3) / 4 * 4 + 4, 0); // whole uint4s for the staging copy
   via.pair.resize((via.pair.size() + 15) / 16 * 16 + 16, 0);
   d.via_words = static_cast<uint32_t>(via.bits.size());
@@ -263,7 +268,7 @@ static int pattern_create_impl(const uint32_t* opc, uint32_t nop, const ugx_pref
   if (rc == UGX_OK) { p->allocs.push_back(d_opc); rc = upload(d_pred, pf->min < 4 ? pf->pma : pf->pmh, UGX_HASH); }
   if (rc == UGX_OK) { p->allocs.push_back(d_pred); rc = upload(d_tap, pf->tap, UGX_BTAP); }
   if (rc == UGX_OK) { p->allocs.push_back(d_tap); rc = upload(d_words, k_word_ranges, sizeof(k_word_ranges)); }
-  if (rc == UGX_OK) { p->allocs.push_back(d_words); rc = upload(d_vids, via.ids, sizeof(via.ids)); }
+  if (rc == UGX_OK) { p->allocs.push_back(d_words); rc = upload(d_vids, via_t.data(), via_t.size() * 4); }
   if (rc == UGX_OK) { p->allocs.push_back(d_vids); rc = upload(d_vbits, via.bits.data(), via.bits.size() * 4); }
   if (rc == UGX_OK) { p->allocs.push_back(d_vbits); rc = upload(d_vpair, via.pair.data(), via.pair.size()); }
   if (rc == UGX_OK) p->allocs.push_back(d_vpair);
@@ -345,10 +350,12 @@ static int plan_describe_impl(const uint32_t* opc, uint32_t nop, const ugx_prefi
   return UGX_OK;
 }
 
-int ugx_viability_describe(const uint32_t* opc, uint32_t nop, uint32_t* k, uint32_t* n, uint32_t* ids, uint8_t* pair,
-                           uint32_t cap_pair, uint32_t* npair, uint32_t* bits, uint32_t cap_words, uint32_t* words)
+int ugx_viability_describe(const uint32_t* opc, uint32_t nop, uint32_t* k, uint32_t* stride, uint32_t* t01, uint32_t* t23,
+                           uint8_t* pair, uint32_t cap_pair, uint32_t* npair, uint32_t* bits, uint32_t cap_words,
+                           uint32_t* words)
 {
-  if (opc == nullptr || nop == 0 || k == nullptr || n == nullptr || ids == nullptr || npair == nullptr || words == nullptr)
+  if (opc == nullptr || nop == 0 || k == nullptr || stride == nullptr || t01 == nullptr || t23 == nullptr ||
+      npair == nullptr || words == nullptr)
     return fail(UGX_E_INVALID, "ugx_viability_describe: null argument");
   try
   {
@@ -360,8 +367,9 @@ int ugx_viability_describe(const uint32_t* opc, uint32_t nop, uint32_t* k, uint3
     ugx::Viability v;
     ugx::build_viability(dfa, v);
     *k = v.k;
-    memcpy(n, v.n, sizeof(v.n));
-    memcpy(ids, v.ids, sizeof(v.ids));
+    *stride = v.stride;
+    memcpy(t01, v.t01, sizeof(v.t01));
+    memcpy(t23, v.t23, sizeof(v.t23));
     *npair = static_cast<uint32_t>(v.pair.size());
     *words = static_cast<uint32_t>(v.bits.size());
     if (v.bits.size() > cap_words || v.pair.size() > cap_pair)

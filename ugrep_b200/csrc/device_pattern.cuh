@@ -39,8 +39,8 @@ struct DevPattern {
   const int* word_ranges;  // [2 * n_word_ranges]
   FilterPlan plan;         // first-stage filter of the position-parallel kernels
   // k-gram viability of an anchored attempt (pattern_host.hpp Viability; span_scan.cu)
-  uint32_t via_k, via_n[4], via_words, via_pair_bytes;
-  const uint32_t* via_ids;   // [256]
+  uint32_t via_k, via_stride, via_words, via_pair_bytes;
+  const uint32_t* via_ids;   // [512] t01 / t23 interleaved: one 64-bit lookup per text byte
   const uint32_t* via_bits;  // [via_words] (a multiple of 4 words)
   const uint8_t* via_pair;   // [via_pair_bytes] (a multiple of 16 bytes)
 };

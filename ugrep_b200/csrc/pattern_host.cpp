@@ -350,10 +350,9 @@ void build_viability(const HostDfa& dfa, Viability& v, uint32_t max_bits)
     return;
   const uint32_t ncls = dfa.ncls;
   auto step = [&](uint32_t s, uint32_t b) -> uint16_t { return dfa.next[static_cast<size_t>(s) * ncls + dfa.cls[b]]; };
-  // ids of a level: bytes that every state of `level` treats alike share an id; returns false when there are too many
-  auto assign_ids = [&](const std::vector<uint32_t>& level, uint32_t shift, std::vector<uint8_t>& reps) -> bool {
+  // ids of a level: bytes that every state of `level` treats alike share an id; false when there are too many
+  auto assign_ids = [&](const std::vector<uint32_t>& level, uint32_t (&ids)[256], std::vector<uint8_t>& reps) -> bool {
     std::map<std::vector<uint16_t>, uint32_t> id_of;
-    uint32_t ids[256];
     reps.clear();
     for (uint32_t b = 0; b < 256; ++b)
     {
@@ -368,11 +367,7 @@ void build_viability(const HostDfa& dfa, Viability& v, uint32_t max_bits)
       }
       ids[b] = it->second;
     }
-    if (reps.size() > 255)
-      return false;
-    for (uint32_t b = 0; b < 256; ++b)
-      v.ids[b] |= ids[b] << shift;
-    return true;
+    return reps.size() <= 255;
   };
   auto targets = [&](const std::vector<uint32_t>& level) {
     std::vector<uint8_t> seen(dfa.nstates, 0);
@@ -389,39 +384,35 @@ void build_viability(const HostDfa& dfa, Viability& v, uint32_t max_bits)
       }
     return out;
   };
-  // ---- first two bytes: pair table
-  std::vector<uint8_t> rep0, rep1;
+  // ---- bytes one and two: the pair table of state codes
+  uint32_t id0[256], id1[256], id2[256] = {0}, id3[256] = {0};
+  std::vector<uint8_t> rep0, rep1, rep2, rep3;
   const std::vector<uint32_t> l0{0u};
-  if (!assign_ids(l0, 0, rep0))
+  if (!assign_ids(l0, id0, rep0))
     return;
   const std::vector<uint32_t> l1 = targets(l0);
-  if (l1.empty() || !assign_ids(l1, 8, rep1) || rep0.size() * rep1.size() > 16384)
-  {
-    memset(v.ids, 0, sizeof(v.ids));
+  if (l1.empty() || !assign_ids(l1, id1, rep1) || rep0.size() * rep1.size() > 16384)
     return;
-  }
-  v.n[0] = static_cast<uint32_t>(rep0.size());
-  v.n[1] = static_cast<uint32_t>(rep1.size());
-  v.pair.assign(static_cast<size_t>(v.n[0]) * v.n[1], 0);
-  std::vector<uint32_t> s2; // distinct live states after two bytes
+  const uint32_t n0 = static_cast<uint32_t>(rep0.size()), n1 = static_cast<uint32_t>(rep1.size());
+  std::vector<uint32_t> s2; // distinct live, not yet accepting states after two bytes
   std::map<uint32_t, uint32_t> s2_id;
-  bool overflow = false;
-  for (uint32_t a = 0; a < v.n[0]; ++a)
-    for (uint32_t b = 0; b < v.n[1]; ++b)
+  std::vector<int> raw(static_cast<size_t>(n0) * n1, 0); // 0 dead, -1 accepted, 1 + index into s2
+  for (uint32_t a = 0; a < n0; ++a)
+    for (uint32_t b = 0; b < n1; ++b)
     {
-      uint8_t code = 0;
+      int code = 0;
       const uint16_t t1 = step(0, rep0[a]);
       if (t1 != DEAD)
       {
         if (dfa.accept[t1] != 0)
-          code = VIA_ACCEPTED;
+          code = -1;
         else
         {
           const uint16_t t2 = step(t1, rep1[b]);
           if (t2 != DEAD)
           {
             if (dfa.accept[t2] != 0)
-              code = VIA_ACCEPTED;
+              code = -1;
             else
             {
               auto it = s2_id.find(t2);
@@ -430,52 +421,58 @@ void build_viability(const HostDfa& dfa, Viability& v, uint32_t max_bits)
                 it = s2_id.emplace(t2, static_cast<uint32_t>(s2.size())).first;
                 s2.push_back(t2);
               }
-              if (it->second + 1 >= VIA_ACCEPTED)
-                overflow = true;
-              code = static_cast<uint8_t>(it->second + 1);
+              code = static_cast<int>(it->second) + 1;
             }
           }
         }
       }
-      v.pair[static_cast<size_t>(a) * v.n[1] + b] = code;
+      raw[static_cast<size_t>(a) * n1 + b] = code;
     }
-  v.k = 2;
-  if (overflow)
+  if (s2.size() > 253)
   {
     // too many states after two bytes for one byte of code: every live pair just stays viable
-    for (auto& c : v.pair)
-      c = c != 0 ? VIA_ACCEPTED : 0;
+    for (auto& c : raw)
+      c = c != 0 ? -1 : 0;
     s2.clear();
   }
-  // ---- bytes three and four: bit table over (state code, id2, id3)
-  std::vector<uint8_t> rep2, rep3;
-  std::vector<uint32_t> l3;
-  const uint32_t saved_ids_mask = 0x0000ffffu;
-  if (!s2.empty() && assign_ids(s2, 16, rep2) && static_cast<uint64_t>(s2.size() + 1) * rep2.size() <= max_bits)
+  v.k = 2;
+  // ---- bytes three and four: a bit table over (state code, id2, id3)
+  uint32_t n2 = 1, n3 = 1;
+  if (!s2.empty() && assign_ids(s2, id2, rep2) && static_cast<uint64_t>(s2.size() + 2) * rep2.size() <= max_bits)
   {
     v.k = 3;
-    v.n[2] = static_cast<uint32_t>(rep2.size());
-    l3 = targets(s2);
-    if (!l3.empty() && assign_ids(l3, 24, rep3) && static_cast<uint64_t>(s2.size() + 1) * rep2.size() * rep3.size() <= max_bits)
+    n2 = static_cast<uint32_t>(rep2.size());
+    const std::vector<uint32_t> l3 = targets(s2);
+    if (!l3.empty() && assign_ids(l3, id3, rep3) && static_cast<uint64_t>(s2.size() + 2) * n2 * rep3.size() <= max_bits &&
+        static_cast<uint64_t>(n2) * rep3.size() <= 0xffff)
     {
       v.k = 4;
-      v.n[3] = static_cast<uint32_t>(rep3.size());
+      n3 = static_cast<uint32_t>(rep3.size());
     }
     else
-      for (uint32_t b = 0; b < 256; ++b)
-        v.ids[b] &= 0x00ffffffu;
+      memset(id3, 0, sizeof(id3));
   }
   else
-    for (uint32_t b = 0; b < 256; ++b)
-      v.ids[b] &= saved_ids_mask;
-  const uint64_t total = static_cast<uint64_t>(s2.size() + 1) * v.n[2] * v.n[3];
+    memset(id2, 0, sizeof(id2));
+  const uint32_t accepted = static_cast<uint32_t>(s2.size()) + 1;
+  v.stride = n2 * n3;
+  v.pair.assign(raw.size(), 0);
+  for (size_t i = 0; i < raw.size(); ++i)
+    v.pair[i] = static_cast<uint8_t>(raw[i] < 0 ? accepted : raw[i]);
+  for (uint32_t b = 0; b < 256; ++b)
+  {
+    v.t01[b] = (id0[b] * n1) | (id1[b] << 16);
+    v.t23[b] = (v.k >= 3 ? id2[b] * n3 : 0u) | ((v.k >= 4 ? id3[b] : 0u) << 16);
+  }
+  const uint64_t total = static_cast<uint64_t>(accepted + 1) * v.stride;
   v.bits.assign((total + 31) / 32, 0);
-  for (uint32_t code = 1; code <= s2.size(); ++code)
-    for (uint32_t c2 = 0; c2 < v.n[2]; ++c2)
-      for (uint32_t c3 = 0; c3 < v.n[3]; ++c3)
+  auto set_bit = [&](uint64_t idx) { v.bits[idx >> 5] |= 1u << (idx & 31); };
+  for (uint32_t code = 1; code <= accepted; ++code)
+    for (uint32_t c2 = 0; c2 < n2; ++c2)
+      for (uint32_t c3 = 0; c3 < n3; ++c3)
       {
         bool ok = true;
-        if (v.k >= 3)
+        if (code != accepted && v.k >= 3)
         {
           const uint16_t t3 = step(s2[code - 1], rep2[c2]);
           if (t3 == DEAD)
@@ -484,10 +481,7 @@ void build_viability(const HostDfa& dfa, Viability& v, uint32_t max_bits)
             ok = step(t3, rep3[c3]) != DEAD;
         }
         if (ok)
-        {
-          const uint64_t idx = (static_cast<uint64_t>(code) * v.n[2] + c2) * v.n[3] + c3;
-          v.bits[idx >> 5] |= 1u << (idx & 31);
-        }
+          set_bit((static_cast<uint64_t>(code) * n2 + c2) * n3 + c3);
       }
 }
 

@@ -45,21 +45,22 @@ struct HostDfa {
   uint32_t table_bytes() const { return nstates * ncls * 2; }
 };
 
-// k-gram viability of an anchored attempt (span_scan.cu): position p can only start a match if the DFA, fed the k bytes
-// at p, accepts on the way or is still alive after them.  Bytes are mapped to small per-level ids (two bytes get the
-// same id at level i when every state reachable after i bytes treats them alike).  Two lookups per position:
-//   code = pair[id0 * n[1] + id1]      0 = dead within two bytes, VIA_ACCEPTED = accepted within two bytes (viable
-//                                      whatever follows), else 1 + the index of the state reached;
-//   bit (code * n[2] + id2) * n[3] + id3 of `bits`: alive (or accepted) after bytes three and four.
+// k-gram viability of an anchored attempt (span_scan.cu, stream_count.cu): position p can only start a match if the DFA,
+// fed the k bytes at p, accepts on the way or is still alive after them.  Bytes are mapped to small per-level ids (two
+// bytes get the same id at level i when every state reachable after i bytes treats them alike); the tables hold the ids
+// pre-multiplied so that the device does two adds and two lookups per position:
+//   code = pair[(t01[b0] & 0xffff) + (t01[b1] >> 16)]      0 = dead within two bytes, 1 + s = the s-th distinct state
+//                                                         reached, `accepted` = accepted within two bytes (a row of ones)
+//   viable = bit (code * stride + (t23[b2] & 0xffff) + (t23[b3] >> 16)) of `bits`
 // k = 0: no table (META edges, accepting start state, too many ids).  A property of the DFA alone: it never changes which
 // positions match, it only spares attempts that cannot.
-constexpr uint8_t VIA_ACCEPTED = 255;
 struct Viability {
   uint32_t k = 0;               // bytes looked at: 0 (none), 2, 3 or 4
-  uint32_t n[4] = {1, 1, 1, 1};
-  uint32_t ids[256] = {0};      // id at level i in bits 8i .. 8i + 7
-  std::vector<uint8_t> pair;    // [n[0] * n[1]]
-  std::vector<uint32_t> bits;
+  uint32_t stride = 1;          // bits per state code: ids at level 2 times ids at level 3
+  uint32_t t01[256] = {0};      // (id0 * n1) | id1 << 16
+  uint32_t t23[256] = {0};      // (id2 * n3) | id3 << 16
+  std::vector<uint8_t> pair;    // [n0 * n1] state codes
+  std::vector<uint32_t> bits;   // [(states + 2) * stride] bits
 };
 void build_viability(const HostDfa& dfa, Viability& v, uint32_t max_bits = 1u << 18);
 

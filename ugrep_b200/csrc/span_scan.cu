@@ -64,7 +64,7 @@ struct SpanMasks {
 // masks of the chunk at `base` (16-byte aligned); positions at or past `limit` read as nothing
 __device__ __forceinline__ SpanMasks eval_masks(const Text& t, const DevPattern& P, const Tables& T, const uint8_t* s_flags,
                                                 const ViaTables& via, uint64_t base, uint64_t limit, bool want_cand,
-                                                bool want_cbk)
+                                                bool want_cbk, bool want_via)
 {
   SpanMasks m;
   m.cand = m.cbk = m.nl = m.via = 0;
@@ -82,7 +82,7 @@ __device__ __forceinline__ SpanMasks eval_masks(const Text& t, const DevPattern&
       m.cbk |= static_cast<uint32_t>(s_flags[UGX_WB(W, k)] & 1u) << k;
   }
   // positions whose next bytes cannot start a match (the last bytes of the buffer are left to the attempt)
-  m.via = (via.on && interior) ? viable16(via, W) : 0xffffu;
+  m.via = (want_via && interior) ? viable16(via, W) : 0xffffu;
   if (base + 16 > limit)
   {
     const uint32_t valid = (1u << (limit - base)) - 1u;
@@ -257,6 +257,8 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
   const uint64_t nregions = (limit + SC_REGION - 1) / SC_REGION;
   const uint64_t total_warps = static_cast<uint64_t>(gridDim.x) * NWARPS;
   uint32_t bad = 0; // bit 0: an attempt failed at the end of the buffer, bit 1: a match too long for the table
+  uint32_t probe_tick = 0;
+  bool via_keep = false;
 
   for (uint64_t r = static_cast<uint64_t>(blockIdx.x) * NWARPS + wid; r < nregions; r += total_warps)
   {
@@ -275,14 +277,20 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
     }
     // masks of the first span to process (the window before the region, or span 0 of region 0) and of the one after
     int s = r == 0 ? 0 : -1;
-    SpanMasks cur = eval_masks(t, P, T, s_flags, via, rb + static_cast<int64_t>(s) * SP_SPAN + lane * 16, limit, !lazy, mask_lb);
+    // The viability table costs two lookups per byte.  The lazy form lives on it; the mask form measures on the first
+    // span of every region how many attempts it spares and keeps it only where that pays (a warp-round of attempts).
+    // (the measurement is repeated every eighth region of a warp; in between its last answer stands)
+    const bool probe_now = via.on && !lazy && (probe_tick++ & 7u) == 0;
+    bool via_r = via.on && (lazy || probe_now || via_keep);
+    bool probing = probe_now;
+    SpanMasks cur = eval_masks(t, P, T, s_flags, via, rb + static_cast<int64_t>(s) * SP_SPAN + lane * 16, limit, !lazy, mask_lb, via_r);
     for (; s < SP_SPANS; ++s)
     {
       const uint64_t sbase = rb + static_cast<int64_t>(s) * SP_SPAN;
       if (sbase >= limit)
         break;
       // ---- 1. masks of the next span (needed now for the carry into this one; they become `cur` afterwards)
-      const SpanMasks nxt = eval_masks(t, P, T, s_flags, via, sbase + SP_SPAN + lane * 16, limit, !lazy, mask_lb);
+      const SpanMasks nxt = eval_masks(t, P, T, s_flags, via, sbase + SP_SPAN + lane * 16, limit, !lazy, mask_lb, via_r);
       // ---- 2. the attempt set of this span (lazy form: the viable positions, membership decided in step 3)
       uint32_t a16 = lazy ? cur.via : cur.cand;
       if (mask_lb)
@@ -306,7 +314,7 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
                 bad |= 4u;
                 break;
               }
-              const SpanMasks far = eval_masks(t, P, T, s_flags, via, fb + lane * 16, limit, true, true);
+              const SpanMasks far = eval_masks(t, P, T, s_flags, via, fb + lane * 16, limit, true, true, false);
               const SpanCarry cf = span_carry(far);
               const uint32_t o0 = cf.out(0);
               if (cf.out(1) == o0)
@@ -324,7 +332,15 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
         a16 = flood16(cur.cand, cur.cbk, cc.into(cin_span, lane), unused);
       }
       if (!lazy)
+      {
+        if (probing)
+        {
+          probing = false;
+          via_keep = __reduce_add_sync(0xffffffffu, __popc(a16 & ~cur.via)) >= 32u;
+          via_r = via_keep;
+        }
         a16 &= cur.via; // a position that cannot start a match needs no attempt (its D is 0 either way)
+      }
       // ---- 3. D(p) for the positions of A: compaction, then ONE loop whose body is a single DFA transition — a lane
       // that finishes an attempt takes its next position in the same iteration, so the lanes keep stepping together
       // whatever the lengths of their attempts

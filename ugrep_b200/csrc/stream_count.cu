@@ -231,6 +231,8 @@ struct DfaEval {
   uint32_t nterms, off0, off1, off2;
   bool use_lut;
   ViaTables via;        // k-gram viability of an attempt: a survivor that cannot start a match is dropped before stage 2
+  mutable uint32_t via_tick = 0; // spans with survivors seen so far; every 64th measures what the table spares ...
+  mutable bool via_keep = true;  // ... and the next 63 use it only if that is worth its two lookups per byte
 
   __device__ __forceinline__ void try_at(uint64_t sbase, uint32_t off, bool exact) const
   {
@@ -328,16 +330,25 @@ struct DfaEval {
       exact = true;
       surv = exact_chunk_candidates(t, P, T, sbase + lane * 16, w[0], w[1], w[2], w[3], w[4], w[5]);
     }
-    if (via.on && interior && surv != 0)
-    {
-      Window W;
-#pragma unroll
-      for (int i = 0; i < 7; ++i)
-        W.w[i] = w[i];
-      surv &= viable16(via, W);
-    }
     if (!__any_sync(0xffffffffu, surv != 0))
       return false;
+    if (via.on && interior)
+    {
+      const bool probe = (via_tick++ & 63u) == 0;
+      if (probe || via_keep)
+      {
+        Window W;
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+          W.w[i] = w[i];
+        const uint32_t v = viable16(via, W);
+        if (probe)
+          via_keep = __reduce_add_sync(0xffffffffu, __popc(surv & ~v)) >= 32u;
+        surv &= v;
+        if (!__any_sync(0xffffffffu, surv != 0))
+          return false;
+      }
+    }
     // ---- compaction + balanced stage 2.  Per round: a warp scan of the lanes' survivor counts; the lanes whose
     // survivors fit into the free part of the 64-entry queue write ALL of them (so a lane holding a run of
     // survivors does not cost one round per survivor); full groups of 32 are then handed out one per lane.

@@ -9,33 +9,31 @@
 namespace ugx {
 
 struct ViaTables {
-  const uint32_t* ids;  // [256] shared
+  const uint2* t;       // [256] shared: (t01, t23) of a byte
   const uint8_t* pair;  // shared
   const uint32_t* bits; // shared
-  uint32_t n1, n2, n3;
+  uint32_t stride;
   bool on;
 };
 
-__host__ __device__ inline uint32_t via_smem_bytes(const DevPattern& P) { return P.via_k ? 1024 + P.via_pair_bytes + P.via_words * 4 : 0; }
+__host__ __device__ inline uint32_t via_smem_bytes(const DevPattern& P) { return P.via_k ? 2048 + P.via_pair_bytes + P.via_words * 4 : 0; }
 
 // stage the tables behind `base` (16-byte aligned); every thread of the CTA calls it; the caller synchronises
 __device__ __forceinline__ ViaTables via_stage(const DevPattern& P, uint8_t* base, bool on)
 {
   ViaTables v;
   v.on = on && P.via_k != 0;
-  v.n1 = P.via_n[1];
-  v.n2 = P.via_n[2];
-  v.n3 = P.via_n[3];
-  uint32_t* ids = reinterpret_cast<uint32_t*>(base);
-  uint32_t* bits = ids + 256;
+  v.stride = P.via_stride;
+  uint32_t* t = reinterpret_cast<uint32_t*>(base);
+  uint32_t* bits = t + 512;
   uint8_t* pair = reinterpret_cast<uint8_t*>(bits + P.via_words);
-  v.ids = ids;
+  v.t = reinterpret_cast<const uint2*>(t);
   v.bits = bits;
   v.pair = pair;
   if (v.on)
   {
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
-      ids[i] = __ldg(P.via_ids + i);
+    for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x)
+      t[i] = __ldg(P.via_ids + i);
     for (uint32_t i = threadIdx.x; i < P.via_words; i += blockDim.x)
       bits[i] = __ldg(P.via_bits + i);
     for (uint32_t i = threadIdx.x; i < P.via_pair_bytes / 4; i += blockDim.x)
@@ -47,20 +45,18 @@ __device__ __forceinline__ ViaTables via_stage(const DevPattern& P, uint8_t* bas
 // viable positions of an interior chunk (all 19 bytes the test reads exist): bit k = position k may start a match
 __device__ __forceinline__ uint32_t viable16(const ViaTables& v, const Window& W)
 {
-  uint32_t i0 = v.ids[UGX_WB(W, 0)], i1 = v.ids[UGX_WB(W, 1)], i2 = v.ids[UGX_WB(W, 2)];
+  uint2 a = v.t[UGX_WB(W, 0)], b = v.t[UGX_WB(W, 1)], c = v.t[UGX_WB(W, 2)];
   uint32_t m = 0;
 #pragma unroll
   for (int k = 0; k < 16; ++k)
   {
-    const uint32_t i3 = v.ids[UGX_WB(W, k + 3)];
-    const uint32_t code = v.pair[(i0 & 0xffu) * v.n1 + ((i1 >> 8) & 0xffu)];
-    const uint32_t c = code == 255u ? 0u : code;
-    const uint32_t idx = (c * v.n2 + ((i2 >> 16) & 0xffu)) * v.n3 + (i3 >> 24);
-    const uint32_t bit = (v.bits[idx >> 5] >> (idx & 31u)) & 1u;
-    m |= (code == 255u ? 1u : (code != 0u ? bit : 0u)) << k;
-    i0 = i1;
-    i1 = i2;
-    i2 = i3;
+    const uint2 d = v.t[UGX_WB(W, k + 3)];
+    const uint32_t code = v.pair[(a.x & 0xffffu) + (b.x >> 16)];
+    const uint32_t idx = code * v.stride + (c.y & 0xffffu) + (d.y >> 16);
+    m |= ((v.bits[idx >> 5] >> (idx & 31u)) & 1u) << k;
+    a = b;
+    b = c;
+    c = d;
   }
   return m;
 }
