@@ -12,8 +12,8 @@
 //
 // How a file is searched:
 //   * the first find() on a new input makes sure the whole input is in memory (mmap'd files already are:
-//     AbstractMatcher::buffer(base, size), absmatcher.h:542-591; streamed inputs are read in full with
-//     AbstractMatcher::buffer(), absmatcher.h:429-461) and hands it to ugx_find_all_device: ONE device scan;
+//     AbstractMatcher::buffer(base, size), absmatcher.h:542-591; streamed inputs are read to their end into the
+//     matcher's own buffer, as peek_more() would block by block) and hands it to ugx_find_all_device: ONE device scan;
 //   * every find() then replays the next record — txt_/len_/cap_/cur_/pos_/got_ as Matcher::match leaves them, and
 //     lno_/lpb_/bol_ advanced the way lineno() would have (absmatcher.h:695-736) without re-reading the text;
 //   * after skip('\n') (the only way ugrep moves the cursor itself, src/ugrep.cpp:3991, 10584, ...) records before
@@ -200,8 +200,22 @@ class B200Matcher : public reflex::Matcher {
   void scan_input()
   {
     fresh_ = false;
-    if (!eof_)
-      (void)buffer(static_cast<size_t>(0)); // read the (rest of the) input in full (absmatcher.h:429-461)
+    // Read the rest of the input in full, the way peek_more() does block by block (absmatcher.h:1612-1631): grow()
+    // shifts out what lies before the current line (calling the caller's handler, keeping lno_ / num_ right) or
+    // enlarges the buffer.  (AbstractMatcher::buffer() is not used: it assumes nothing has been read yet, and
+    // Grep::init_is_binary has usually peeked at the first block by now, src/ugrep.cpp:3998-4017.)
+    txt_ = buf_ + cur_;
+    len_ = 0;
+    while (!eof_)
+    {
+      if (end_ + blk_ + 1 >= max_)
+        (void)grow();
+      const size_t n = get(buf_ + end_, blk_ > 0 ? blk_ : max_ - end_ - 1);
+      if (n == 0)
+        eof_ = !wrap();
+      else
+        end_ += n;
+    }
     // records number lines from the start of buf_; lno_ is the line of lpb_ (absmatcher.h:695-736)
     size_t before = 0;
     for (const char *s = buf_; s < lpb_; ++s)
