@@ -209,6 +209,36 @@ int  ugx_find_all_device(ugx_scanner *s, const ugx_pattern *p, const void *buf, 
 int  ugx_scanner_fetch(ugx_scanner *s, ugx_match *out, uint64_t first, uint64_t count);
 int  ugx_count_newlines(ugx_scanner *s, const void *buf, uint64_t nbytes, ugx_totals *totals);
 
+/*
+ * One process, several GPUs: the buffer is cut into one line-aligned shard per device (forward from
+ * n*r/N to the next newline), every device scans its shard, and the per-shard {matches, newlines} give the totals and
+ * the record / line-number bases.  Replaces the reference's per-file worker pool (GrepMaster / GrepWorker,
+ * src/ugrep.cpp:4118-4432) for one large input.  `devices` may name a device more than once.
+ */
+typedef struct ugx_sharded ugx_sharded;
+enum { UGX_MODE_LINES = 0, UGX_MODE_MATCHES = 1, UGX_MODE_RECORDS = 2 }; /* ugrep -c | -c -o | -o -n -b */
+typedef struct ugx_shard {
+  int32_t  device;
+  uint32_t reserved;
+  uint64_t begin, end;       /* the shard is buf[begin, end) */
+  uint64_t matches, newlines;
+  uint64_t line_base;        /* newlines before the shard */
+  uint64_t record_base;      /* matches before the shard */
+  float    kernel_ms;
+  uint32_t reserved2;
+} ugx_shard;
+int  ugx_sharded_create(const uint32_t *opc, uint32_t nop, const ugx_prefilter *pf, uint32_t matcher_flags,
+                        const int *devices, int ndev, ugx_sharded **out);
+void ugx_sharded_destroy(ugx_sharded *s);
+/* "pin": page-lock the caller's buffer during a scan (pays when the same buffer is scanned repeatedly);
+ * every other name is passed to each device's scanner (ugx_scanner_set_option) */
+int  ugx_sharded_set_option(ugx_sharded *s, const char *name, int value);
+/* host_buf: host memory.  mode UGX_MODE_RECORDS writes the records of all shards to out[cap] in input order, offsets
+ * and line numbers global; shards[ndev] (optional) receives what every device did */
+int  ugx_sharded_scan(ugx_sharded *s, const void *host_buf, uint64_t nbytes, int mode, ugx_match *out, uint64_t cap,
+                      uint64_t *n_out, ugx_totals *totals, ugx_shard *shards);
+const char *ugx_sharded_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

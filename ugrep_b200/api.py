@@ -27,7 +27,7 @@ ADVANCE_NAMES = ["none", "pin1_one", "pin1_pma", "pin1_pmh", "pin_one", "pin_pma
 
 EXPORTS = ["ugx_last_error", "ugx_kernel_name", "ugx_plan_describe", "ugx_abi_version", "ugx_pattern_create", "ugx_pattern_load", "ugx_pattern_info_get",
            "ugx_pattern_destroy", "ugx_scanner_create", "ugx_scanner_destroy", "ugx_count_lines", "ugx_count_matches",
-           "ugx_viability_describe", "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_scanner_set_option", "ugx_count_newlines"]
+           "ugx_viability_describe", "ugx_sharded_create", "ugx_sharded_destroy", "ugx_sharded_set_option", "ugx_sharded_scan", "ugx_sharded_last_error", "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_scanner_set_option", "ugx_count_newlines"]
 
 
 class UgxError(RuntimeError):
@@ -211,6 +211,82 @@ class Scanner:
     def close(self):
         if self._h:
             lib().ugx_scanner_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Shard(C.Structure):
+    _fields_ = [("device", C.c_int32), ("reserved", C.c_uint32), ("begin", C.c_uint64), ("end", C.c_uint64),
+                ("matches", C.c_uint64), ("newlines", C.c_uint64), ("line_base", C.c_uint64), ("record_base", C.c_uint64),
+                ("kernel_ms", C.c_float), ("reserved2", C.c_uint32)]
+
+
+def read_ugxp(path: str):
+    """(opcode words, prefilter bytes, matcher flags) of a UGXP pattern file (include/ugrep_b200.h ugx_file_header)"""
+    raw = open(path, "rb").read()
+    if raw[:8] != b"UGXP\x01\x00\x00\x00":
+        raise UgxError(6, "not a UGXP pattern file: %s" % path)
+    nop, _, pfsize, flags = np.frombuffer(raw, dtype="<u4", count=4, offset=8)
+    pf = raw[24:24 + int(pfsize)]
+    opc = np.frombuffer(raw, dtype="<u4", count=int(nop), offset=24 + int(pfsize)).copy()
+    return opc, pf, int(flags)
+
+
+class Sharded:
+    """One process, several GPUs: ugx_sharded_* (line-aligned shards of one host buffer, one device each)."""
+
+    MODES = {"lines": 0, "matches": 1, "records": 2}
+
+    def __init__(self, pattern_path: str, devices):
+        L = lib()
+        L.ugx_sharded_create.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int,
+                                         C.POINTER(C.c_void_p)]
+        L.ugx_sharded_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64,
+                                       C.POINTER(C.c_uint64), C.POINTER(_Totals), C.c_void_p]
+        L.ugx_sharded_destroy.argtypes = [C.c_void_p]
+        L.ugx_sharded_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.ugx_sharded_last_error.restype = C.c_char_p
+        opc, pf, flags = read_ugxp(pattern_path)
+        self.devices = list(devices)
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        self._h = C.c_void_p()
+        rc = L.ugx_sharded_create(opc.ctypes.data, len(opc), pf, flags, devs, len(self.devices), C.byref(self._h))
+        if rc != 0:
+            raise UgxError(rc, L.ugx_sharded_last_error().decode("utf-8", "replace"))
+
+    def set_option(self, name: str, value: int) -> None:
+        rc = lib().ugx_sharded_set_option(self._h, name.encode(), int(value))
+        if rc != 0:
+            raise UgxError(rc, lib().ugx_sharded_last_error().decode("utf-8", "replace"))
+
+    def scan(self, data, mode: str = "lines", cap: int | None = None):
+        """-> (totals, records or None, per-shard info)"""
+        ptr, n, keep = _buffer(data)
+        if hasattr(keep, "is_cuda"):
+            raise TypeError("ugx_sharded_scan takes host memory")
+        t = _Totals()
+        shards = (_Shard * len(self.devices))()
+        cnt = C.c_uint64()
+        out = None
+        m = self.MODES[mode]
+        if m == 2:
+            out = np.zeros(cap if cap is not None else max(1024, n // 8), dtype=MATCH_DTYPE)
+        rc = lib().ugx_sharded_scan(self._h, C.c_void_p(ptr), n, m, out.ctypes.data if out is not None else None,
+                                    len(out) if out is not None else 0, C.byref(cnt), C.byref(t), shards)
+        if rc != 0:
+            raise UgxError(rc, lib().ugx_sharded_last_error().decode("utf-8", "replace"))
+        info = [{f: getattr(sh, f) for f, _ in _Shard._fields_ if not f.startswith("reserved")} for sh in shards]
+        tot = Totals(t.matches, t.newlines, t.long_lines, t.kernel_ms, t.launches, lib().ugx_kernel_name(t.kernel).decode())
+        return tot, (out[:cnt.value] if out is not None else None), info
+
+    def close(self):
+        if self._h:
+            lib().ugx_sharded_destroy(self._h)
             self._h = None
 
     def __del__(self):
