@@ -137,6 +137,8 @@ typedef struct ugx_plan_info {
   uint32_t lut[256];
 } ugx_plan_info;
 
+enum { UGX_MODE_LINES = 0, UGX_MODE_MATCHES = 1, UGX_MODE_RECORDS = 2 }; /* ugrep -c | -c -o | -o -n -b */
+
 typedef struct ugx_pattern ugx_pattern; /* immutable once created; shareable between host threads */
 typedef struct ugx_scanner ugx_scanner; /* per host thread / per stream scratch (counters, record arena) */
 
@@ -152,7 +154,7 @@ typedef struct ugx_totals {
 
 /* scan kernels (reported in ugx_totals.kernel) */
 enum { UGX_K_NONE = 0, UGX_K_STREAM_LITERAL = 1, UGX_K_STREAM_DFA = 2, UGX_K_TILE_ANY = 3, UGX_K_LINE_SCAN = 4,
-       UGX_K_RECORDS = 5, UGX_K_NEWLINES = 6, UGX_K_MATCH_LINES = 7, UGX_K_SPAN = 8 };
+       UGX_K_RECORDS = 5, UGX_K_NEWLINES = 6, UGX_K_MATCH_LINES = 7, UGX_K_SPAN = 8, UGX_K_BATCH = 9 };
 
 const char *ugx_last_error(void);
 const char *ugx_kernel_name(uint32_t id);
@@ -210,13 +212,34 @@ int  ugx_scanner_fetch(ugx_scanner *s, ugx_match *out, uint64_t first, uint64_t 
 int  ugx_count_newlines(ugx_scanner *s, const void *buf, uint64_t nbytes, ugx_totals *totals);
 
 /*
+ * Many files in one launch: what the reference's per-file job queue feeds its workers (GrepMaster::submit /
+ * GrepWorker::execute, src/ugrep.cpp:4295-4432).  The files lie in one buffer (host or device), file i at
+ * buf[begins[i], begins[i] + lens[i]) with every begins[i] a multiple of 16 (the bytes between files are never read as
+ * text); counts[i] receives what `ugrep -c` (UGX_MODE_LINES) or `ugrep -c -o` (UGX_MODE_MATCHES) prints for file i
+ * scanned on its own: each file keeps its own end of buffer.  totals->matches is the sum.
+ */
+int  ugx_count_batch(ugx_scanner *s, const ugx_pattern *p, const void *buf, uint64_t nbytes,
+                     const uint64_t *begins, const uint64_t *lens, uint64_t nfiles, int mode,
+                     uint64_t *counts, ugx_totals *totals);
+
+/* what ugrep asks about a file before it prints from it (Grep::init_is_binary, src/ugrep.cpp:3998-4017):
+ * is_utf8 = reflex::isutf8 (lib/simd.cpp:169-421: valid UTF-8 structure, no NUL), has_nul = memchr(buf, 0, n) != NULL;
+ * is_binary() is !is_utf8 by default and has_nul with -U (src/ugrep.cpp:699-711) */
+typedef struct ugx_text_info {
+  uint32_t is_utf8;
+  uint32_t has_nul;
+  float    kernel_ms;
+  uint32_t launches;
+} ugx_text_info;
+int  ugx_check_text(ugx_scanner *s, const void *buf, uint64_t nbytes, ugx_text_info *out);
+
+/*
  * One process, several GPUs: the buffer is cut into one line-aligned shard per device (forward from
  * n*r/N to the next newline), every device scans its shard, and the per-shard {matches, newlines} give the totals and
  * the record / line-number bases.  Replaces the reference's per-file worker pool (GrepMaster / GrepWorker,
  * src/ugrep.cpp:4118-4432) for one large input.  `devices` may name a device more than once.
  */
 typedef struct ugx_sharded ugx_sharded;
-enum { UGX_MODE_LINES = 0, UGX_MODE_MATCHES = 1, UGX_MODE_RECORDS = 2 }; /* ugrep -c | -c -o | -o -n -b */
 typedef struct ugx_shard {
   int32_t  device;
   uint32_t reserved;

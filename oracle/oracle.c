@@ -845,6 +845,37 @@ int ora_find_all(const ora_pattern *p, const uint8_t *buf, uint64_t n, uint64_t 
   return c > cap ? UGX_E_OVERFLOW : UGX_OK;
 }
 
+/*
+ * reflex::isutf8, lib/simd.cpp:169-421 (scalar form :396-418; the SSE2 / AVX2 / NEON loops, lib/simd_avx2.cpp:82-149,
+ * apply the same rule 16 / 32 bytes at a time): no NUL, no byte C0 C1 F5..FF, a lead byte C2..DF / E0..EF / F0..F4 is
+ * followed by exactly 1 / 2 / 3 continuation bytes 80..BF, no continuation byte anywhere else, no sequence cut off by
+ * the end.  (Overlong 3- and 4-byte forms and surrogates pass: the reference calls its test "quick".)
+ * ugrep uses it as its binary-file test: is_binary() = !isutf8(), src/ugrep.cpp:699-711.
+ */
+int ora_isutf8(const uint8_t *buf, uint64_t n)
+{
+  uint64_t i = 0;
+  while (i < n)
+  {
+    int c = (int8_t)buf[i];
+    if (c > 0)
+    {
+      ++i;
+      continue;
+    }
+    ++i;
+    if (c < -62 || c > -12 || i >= n || (buf[i++] & 0xc0) != 0x80)
+      return 0;
+    if (c >= -32 && (i >= n || (buf[i++] & 0xc0) != 0x80))
+      return 0;
+    if (c >= -16 && (i >= n || (buf[i++] & 0xc0) != 0x80))
+      return 0;
+  }
+  return 1;
+}
+
+int ora_has_nul(const uint8_t *buf, uint64_t n) { return n > 0 && memchr(buf, 0, (size_t)n) != NULL; }
+
 uint64_t ora_count_newlines(const uint8_t *buf, uint64_t n)
 {
   uint64_t c = 0;

@@ -35,6 +35,9 @@ int  ora_find_all(const ora_pattern *p, const uint8_t *buf, uint64_t n,
                   uint64_t base_offset, uint64_t base_line,
                   ugx_match *out, uint64_t cap, uint64_t *n_out);
 uint64_t ora_count_newlines(const uint8_t *buf, uint64_t n);
+/* reflex::isutf8 (lib/simd.cpp:169-421): ugrep's binary-file test is !isutf8 */
+int  ora_isutf8(const uint8_t *buf, uint64_t n);
+int  ora_has_nul(const uint8_t *buf, uint64_t n);
 
 /* prefilter alone: bit k of bitmap (little-endian within bytes) = position k is a candidate */
 int  ora_candidates(const ora_pattern *p, const uint8_t *buf, uint64_t n, uint8_t *bitmap);

@@ -12,6 +12,7 @@
 //        (AbstractMatcher::buffer, absmatcher.h:542-591) with the caller loops
 //        of Grep::search (src/ugrep.cpp:10536-10586, :10857-11047) and print
 //        what `ugrep -c`, `ugrep -c -o`, `ugrep -n -b -o` print.
+//   refscan isutf8 FILE...                 reflex::isutf8 (ugrep's binary-file test) per file
 //   refscan bench MODE [popts] -J N -r R FILE   time R repetitions of the scan
 //        over N line-aligned shards on N threads (one cloned matcher each, as
 //        GrepWorker does, src/ugrep.cpp:4204-4215); prints seconds (best).
@@ -22,6 +23,7 @@
 // Built with -fno-access-control so the dump can read Pattern's tables.
 #include <reflex/matcher.h>
 #include <reflex/pattern.h>
+#include <reflex/simd.h>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -312,6 +314,18 @@ int main(int argc, char **argv)
         return 2;
       }
       return do_dump(o, out);
+    }
+    if (cmd == "isutf8")
+    {
+      // reflex::isutf8 (lib/simd.cpp:169) over every file named: one 0/1 per line
+      for (int i = 2; i < argc; ++i)
+      {
+        std::vector<char> data;
+        if (!read_file(argv[i], data))
+          return 2;
+        printf("%d\n", reflex::isutf8(data.data(), data.data() + data.size() - 1) ? 1 : 0);
+      }
+      return 0;
     }
     if (cmd == "scan" || cmd == "bench")
     {

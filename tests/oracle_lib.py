@@ -54,6 +54,8 @@ def lib():
                                    C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.ora_count_newlines.argtypes = [C.c_void_p, C.c_uint64]
         L.ora_count_newlines.restype = C.c_uint64
+        L.ora_isutf8.argtypes = [C.c_void_p, C.c_uint64]
+        L.ora_has_nul.argtypes = [C.c_void_p, C.c_uint64]
         L.ora_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.ora_match_at.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib = L
@@ -124,6 +126,16 @@ class OraclePattern:
 def newlines(data) -> int:
     a = _as_u8(data)
     return lib().ora_count_newlines(a.ctypes.data, a.size)
+
+
+def isutf8(data) -> bool:
+    a = _as_u8(data)
+    return bool(lib().ora_isutf8(a.ctypes.data, a.size))
+
+
+def has_nul(data) -> bool:
+    a = _as_u8(data)
+    return bool(lib().ora_has_nul(a.ctypes.data, a.size))
 
 
 # ---- the unmodified reference (oracle/_ref) ----

@@ -27,7 +27,7 @@ ADVANCE_NAMES = ["none", "pin1_one", "pin1_pma", "pin1_pmh", "pin_one", "pin_pma
 
 EXPORTS = ["ugx_last_error", "ugx_kernel_name", "ugx_plan_describe", "ugx_abi_version", "ugx_pattern_create", "ugx_pattern_load", "ugx_pattern_info_get",
            "ugx_pattern_destroy", "ugx_scanner_create", "ugx_scanner_destroy", "ugx_count_lines", "ugx_count_matches",
-           "ugx_viability_describe", "ugx_sharded_create", "ugx_sharded_destroy", "ugx_sharded_set_option", "ugx_sharded_scan", "ugx_sharded_last_error", "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_scanner_set_option", "ugx_count_newlines"]
+           "ugx_viability_describe", "ugx_check_text", "ugx_count_batch", "ugx_sharded_create", "ugx_sharded_destroy", "ugx_sharded_set_option", "ugx_sharded_scan", "ugx_sharded_last_error", "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_scanner_set_option", "ugx_count_newlines"]
 
 
 class UgxError(RuntimeError):
@@ -39,6 +39,10 @@ class UgxError(RuntimeError):
 class _Totals(C.Structure):
     _fields_ = [("matches", C.c_uint64), ("newlines", C.c_uint64), ("long_lines", C.c_uint64),
                 ("kernel_ms", C.c_float), ("launches", C.c_uint32), ("kernel", C.c_uint32)]
+
+
+class _TextInfo(C.Structure):
+    _fields_ = [("is_utf8", C.c_uint32), ("has_nul", C.c_uint32), ("kernel_ms", C.c_float), ("launches", C.c_uint32)]
 
 
 class _Info(C.Structure):
@@ -177,6 +181,34 @@ class Scanner:
         t = _Totals()
         _check(lib().ugx_count_newlines(self._h, C.c_void_p(ptr), n, C.byref(t)))
         return self._totals(t)
+
+    def count_batch(self, pattern: Pattern, files: list, mode: str = "lines"):
+        """`ugrep -c` / `ugrep -c -o` of many files in ONE launch: (per-file counts, totals).  The files (bytes-like)
+        are packed back to back on 16-byte boundaries into one host buffer, as a batching feeder would."""
+        begins = np.zeros(len(files), dtype=np.uint64)
+        lens = np.array([len(f) for f in files], dtype=np.uint64)
+        at = 0
+        for i, f in enumerate(files):
+            begins[i] = at
+            at = (at + len(f) + 15) & ~15
+        pack = np.full(max(at, 16), 0x58, dtype=np.uint8)
+        for i, f in enumerate(files):
+            pack[int(begins[i]):int(begins[i]) + len(f)] = np.frombuffer(bytes(f), dtype=np.uint8)
+        counts = np.zeros(max(1, len(files)), dtype=np.uint64)
+        t = _Totals()
+        lib().ugx_count_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                          C.c_uint64, C.c_int, C.c_void_p, C.POINTER(_Totals)]
+        _check(lib().ugx_count_batch(self._h, pattern._h, pack.ctypes.data, pack.size, begins.ctypes.data, lens.ctypes.data,
+                                     len(files), 0 if mode == "lines" else 1, counts.ctypes.data, C.byref(t)))
+        return counts[:len(files)], self._totals(t)
+
+    def check_text(self, data) -> dict:
+        """reflex::isutf8 / NUL test over the buffer (ugrep's binary-file detection)"""
+        ptr, n, keep = _buffer(data)
+        t = _TextInfo()
+        lib().ugx_check_text.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(_TextInfo)]
+        _check(lib().ugx_check_text(self._h, C.c_void_p(ptr), n, C.byref(t)))
+        return {"is_utf8": bool(t.is_utf8), "has_nul": bool(t.has_nul), "kernel_ms": t.kernel_ms}
 
     def find_all_device(self, pattern: Pattern, data, base_offset: int = 0, base_line: int = 0) -> Totals:
         """Like find_all but the records stay on the device (fetch() copies a range to the host)."""

@@ -130,6 +130,8 @@ struct ugx_scanner {
   // span scan scratch
   uint64_t* span_regions = nullptr; // [5 * regions]
   uint64_t span_regions_cap = 0;
+  uint64_t* batch = nullptr;      // ugx_count_batch: file table, counters, tile table
+  uint64_t batch_cap = 0;
   bool no_span = false;           // counting matches / records take the line-at-a-time kernels (A/B timing, tests)
 };
 
@@ -500,6 +502,7 @@ void ugx_scanner_destroy(ugx_scanner* s)
   cudaFreeHost(s->h_totals);
   cudaFree(s->region_sum);
   cudaFree(s->span_regions);
+  cudaFree(s->batch);
   cudaFree(s->tile_base);
   cudaFree(s->rec_stage);
   cudaFree(s->partials);
@@ -977,6 +980,7 @@ const char* ugx_kernel_name(uint32_t id)
     case UGX_K_NEWLINES: return "count_newlines_kernel";
     case UGX_K_MATCH_LINES: return "match_lines_kernel";
     case UGX_K_SPAN: return "span_scan_kernel";
+    case UGX_K_BATCH: return "scan_batch_kernel";
     default: return "none";
   }
 }
@@ -1039,6 +1043,122 @@ int ugx_scanner_fetch(ugx_scanner* s, ugx_match* out, uint64_t first, uint64_t c
   CU(cudaSetDevice(s->device));
   CU(cudaMemcpyAsync(out, s->records + first, count * sizeof(ugx_match), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
+  return UGX_OK;
+}
+
+int ugx_count_batch(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t nbytes, const uint64_t* begins,
+                    const uint64_t* lens, uint64_t nfiles, int mode, uint64_t* counts, ugx_totals* totals)
+{
+  if (s == nullptr || p == nullptr || (buf == nullptr && nbytes != 0) || (nfiles != 0 && (begins == nullptr || lens == nullptr || counts == nullptr)) ||
+      (mode != UGX_MODE_LINES && mode != UGX_MODE_MATCHES))
+    return fail(UGX_E_INVALID, "ugx_count_batch: bad argument");
+  if (s->device != p->device)
+    return fail(UGX_E_INVALID, "pattern and scanner live on different devices");
+  ugx_totals tt;
+  memset(&tt, 0, sizeof(tt));
+  if (totals)
+    *totals = tt;
+  if (nfiles == 0)
+    return UGX_OK;
+  try
+  {
+    // the tile table: tile g of the launch is tile tile_index[g] of file tile_file[g]
+    std::vector<uint32_t> tf, ti;
+    for (uint64_t f = 0; f < nfiles; ++f)
+    {
+      if ((begins[f] & 15) != 0 || begins[f] > nbytes || lens[f] > nbytes - begins[f])
+        return fail(UGX_E_INVALID, "ugx_count_batch: file " + std::to_string(f) + " is not a 16-byte aligned range of the buffer");
+      if (nfiles > 0xffffffffull || lens[f] / ugx::SCAN_TILE > 0xfffffffeull)
+        return fail(UGX_E_INVALID, "ugx_count_batch: too many files / a file too large for one batch");
+      const uint64_t nt = (lens[f] + ugx::SCAN_TILE - 1) / ugx::SCAN_TILE;
+      for (uint64_t j = 0; j < nt; ++j)
+      {
+        tf.push_back(static_cast<uint32_t>(f));
+        ti.push_back(static_cast<uint32_t>(j));
+      }
+    }
+    memset(counts, 0, nfiles * sizeof(uint64_t));
+    if (tf.empty() || p->never)
+      return UGX_OK; // only empty files, or a prefilter that admits no candidate (config 3): nothing matches
+    CU(cudaSetDevice(s->device));
+    const uint8_t* dbuf = nullptr;
+    uint64_t h2d = 0;
+    int rc = resolve(s, buf, nbytes, &dbuf, &h2d);
+    if (rc != UGX_OK)
+      return rc;
+    // one scratch block: begins | lens | counts | tile_file | tile_index
+    const uint64_t words = 3 * nfiles + (tf.size() + 1) / 2 * 2;
+    rc = ensure(s->batch, s->batch_cap, words + 4);
+    if (rc != UGX_OK)
+      return rc;
+    uint64_t* d_begins = s->batch;
+    uint64_t* d_lens = d_begins + nfiles;
+    unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(d_lens + nfiles);
+    uint32_t* d_tf = reinterpret_cast<uint32_t*>(d_counts + nfiles);
+    uint32_t* d_ti = d_tf + tf.size();
+    CU(cudaMemcpyAsync(d_begins, begins, nfiles * 8, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(d_lens, lens, nfiles * 8, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemsetAsync(d_counts, 0, nfiles * 8, s->stream));
+    CU(cudaMemcpyAsync(d_tf, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(d_ti, ti.data(), ti.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    ugx::BatchArgs a;
+    a.begins = d_begins;
+    a.lens = d_lens;
+    a.tile_file = d_tf;
+    a.tile_index = d_ti;
+    a.ntiles = tf.size();
+    a.counts = d_counts;
+    a.stage_table = 0;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    CU(ugx::launch_scan_batch(p->dev, dbuf, a, mode, s->sm_count, s->stream));
+    CU(cudaEventRecord(s->ev1, s->stream));
+    CU(cudaMemcpyAsync(counts, d_counts, nfiles * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    for (uint64_t f = 0; f < nfiles; ++f)
+      tt.matches += counts[f];
+    tt.kernel_ms = ms;
+    tt.launches = 1;
+    tt.kernel = UGX_K_BATCH;
+    if (totals)
+      *totals = tt;
+    return UGX_OK;
+  }
+  catch (const std::bad_alloc&)
+  {
+    return fail(UGX_E_NOMEM, "out of host memory");
+  }
+}
+
+int ugx_check_text(ugx_scanner* s, const void* buf, uint64_t nbytes, ugx_text_info* out)
+{
+  if (s == nullptr || out == nullptr || (buf == nullptr && nbytes != 0))
+    return fail(UGX_E_INVALID, "null argument");
+  memset(out, 0, sizeof(*out));
+  out->is_utf8 = 1;
+  if (nbytes == 0)
+    return UGX_OK;
+  CU(cudaSetDevice(s->device));
+  const uint8_t* dbuf = nullptr;
+  uint64_t h2d = 0;
+  const int rc = resolve(s, buf, nbytes, &dbuf, &h2d);
+  if (rc != UGX_OK)
+    return rc;
+  unsigned int* dflags = reinterpret_cast<unsigned int*>(s->totals + 7);
+  CU(cudaMemsetAsync(dflags, 0, sizeof(unsigned long long), s->stream));
+  CU(cudaEventRecord(s->ev0, s->stream));
+  CU(ugx::launch_utf8_check(dbuf, nbytes, dflags, s->sm_count, s->stream));
+  CU(cudaMemcpyAsync(s->h_totals + 7, s->totals + 7, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaEventRecord(s->ev1, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+  const unsigned int f = static_cast<unsigned int>(s->h_totals[7]);
+  out->is_utf8 = (f & 1u) == 0;
+  out->has_nul = (f & 2u) != 0;
+  out->kernel_ms = ms;
+  out->launches = 1;
   return UGX_OK;
 }
 

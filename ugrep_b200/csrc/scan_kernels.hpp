@@ -118,6 +118,21 @@ cudaError_t launch_span_final(const DevPattern& P, const uint8_t* buf, uint64_t 
 // reflex::nlcount (newline_count.cu)
 cudaError_t launch_count_newlines(const uint8_t* buf, uint64_t n, unsigned long long* total, int sm_count, cudaStream_t st);
 
+// ---- many files in one launch (batch_kernel.cu) ----
+struct BatchArgs {
+  const uint64_t* begins;        // [nfiles] device: offset of every file in the batch buffer (multiples of 16)
+  const uint64_t* lens;          // [nfiles] device: its length
+  const uint32_t* tile_file;     // [ntiles] device: the file a tile belongs to
+  const uint32_t* tile_index;    // [ntiles] device: its index within that file
+  uint64_t ntiles;
+  unsigned long long* counts;    // [nfiles] device, zeroed by the caller
+  uint32_t stage_table;          // set by the launcher
+};
+cudaError_t launch_scan_batch(const DevPattern& P, const uint8_t* buf, BatchArgs a, int mode, int sm_count, cudaStream_t st);
+
+// reflex::isutf8 / NUL test (utf8_check.cu): flags bit 0 = not UTF-8 by the reference's rule, bit 1 = has a NUL
+cudaError_t launch_utf8_check(const uint8_t* buf, uint64_t n, unsigned int* flags, int sm_count, cudaStream_t st);
+
 cudaError_t launch_tile_prefix(uint64_t* tile_matches, uint64_t* tile_newlines, uint64_t ntiles,
                                unsigned long long* totals, cudaStream_t st);
 
