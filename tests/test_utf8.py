@@ -53,7 +53,7 @@ def test_gpu_check_text_equals_reference_vectors_and_oracle():
     for data, want in cases():
         got = sc.check_text(data)
         assert got["is_utf8"] == want, data[:60]
-        assert got["has_nul"] == (b"\\x00" in data), data[:60]
+        assert got["has_nul"] == (0 in data), data[:60]
     # sequences cut by every span / chunk boundary, device-resident and misaligned views
     text = corpus.block("c4", 3 << 20)
     dev = torch.from_numpy(text).cuda()
