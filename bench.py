@@ -309,7 +309,8 @@ def main():
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     if world > 1:
-        counts = sharding.all_gather_counts(tot.matches, tot.newlines, device="cuda")
+        # (the streaming `-c` kernels do not count newlines unless asked: the line-number bases come from nlcount)
+        counts = sharding.all_gather_counts(tot.matches, sc.count_newlines(corpus_dev).newlines, device="cuda")
         total_matches = sum(c[0] for c in counts)
     else:
         total_matches = tot.matches

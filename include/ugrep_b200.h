@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define UGX_ABI_VERSION 1
+#define UGX_ABI_VERSION 2
 
 /* status codes (0 = ok; nothing ever falls back to the CPU) */
 enum {
@@ -145,12 +145,19 @@ typedef struct ugx_scanner ugx_scanner; /* per host thread / per stream scratch 
 /* totals every scan reports */
 typedef struct ugx_totals {
   uint64_t matches;        /* count-lines: matching lines; otherwise: matches */
-  uint64_t newlines;       /* '\n' bytes in the buffer (line-number base for the next shard) */
-  uint64_t long_lines;     /* lines that took the long-line path */
+  uint64_t newlines;       /* '\n' bytes in the buffer (line-number base for the next shard); valid when flags has
+                              UGX_TOT_NEWLINES: every call except ugx_count_lines on its streaming kernels, which
+                              count newlines only with the scanner option "count_newlines" */
+  uint64_t flags;          /* UGX_TOT_* */
   float    kernel_ms;      /* device time of the scan kernels (CUDA events on the scan stream) */
   uint32_t launches;       /* kernels launched by this call */
   uint32_t kernel;         /* UGX_K_*: the scan kernel that did the work (ugx_kernel_name) */
 } ugx_totals;
+
+#define UGX_TOT_NEWLINES      1u /* `newlines` was counted by this call */
+#define UGX_TOT_SPAN_HANDOVER 2u /* the span kernels could not vouch for this buffer (a match longer than a window across
+                                    a region start in a line without newlines, a look-back run or match beyond their
+                                    bounds, a failed attempt at the very end): the line-at-a-time kernels did the scan */
 
 /* scan kernels (reported in ugx_totals.kernel) */
 enum { UGX_K_NONE = 0, UGX_K_STREAM_LITERAL = 1, UGX_K_STREAM_DFA = 2, UGX_K_TILE_ANY = 3, UGX_K_LINE_SCAN = 4,

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, n), "libugrep_b200.so does not export %s" % n
     from ugrep_b200 import api
     assert set(api.EXPORTS) == set(names)
-    assert lib.ugx_abi_version() == 1
+    assert lib.ugx_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():

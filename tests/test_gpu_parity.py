@@ -417,10 +417,21 @@ def test_span_kernels_hand_over_what_they_cannot_vouch_for(gpu):
         op = O.OraclePattern(path)
         rec, tot = sc.find_all(pat, data)
         assert same(rec, op.find_all(data)), name
-        assert sc.count_matches(pat, data).matches == op.count_matches(data), name
+        assert tot.flags & 2 and tot.kernel != "span_scan_kernel", name   # UGX_TOT_SPAN_HANDOVER
+        t = sc.count_matches(pat, data)
+        assert t.matches == op.count_matches(data) and t.flags & 1 and t.newlines == data.count(b"\n"), name
     # ... and the ordinary case does stay with the spans
     pat = api.Pattern.load(os.path.join(PAT_DIR, "c5.ugxp"), 0)
-    assert sc.count_matches(pat, corpus.block("c5", 1 << 20)).kernel == "span_scan_kernel"
+    t = sc.count_matches(pat, corpus.block("c5", 1 << 20))
+    assert t.kernel == "span_scan_kernel" and t.flags == 1
+    # ugx_count_lines on its streaming kernels reports newlines only when asked to count them (flag UGX_TOT_NEWLINES)
+    pat2 = api.Pattern.load(os.path.join(PAT_DIR, "c2.ugxp"), 0)
+    blk = corpus.block("c2", 1 << 20)
+    assert sc.count_lines(pat2, blk).flags & 1 == 0
+    sc.set_option("count_newlines", 1)
+    t = sc.count_lines(pat2, blk)
+    assert t.flags & 1 and t.newlines == int((blk == 10).sum())
+    sc.set_option("count_newlines", 0)
 
 
 def test_scanners_on_two_host_threads_share_a_pattern(gpu):

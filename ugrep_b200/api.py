@@ -37,7 +37,7 @@ class UgxError(RuntimeError):
 
 
 class _Totals(C.Structure):
-    _fields_ = [("matches", C.c_uint64), ("newlines", C.c_uint64), ("long_lines", C.c_uint64),
+    _fields_ = [("matches", C.c_uint64), ("newlines", C.c_uint64), ("flags", C.c_uint64),
                 ("kernel_ms", C.c_float), ("launches", C.c_uint32), ("kernel", C.c_uint32)]
 
 
@@ -54,7 +54,7 @@ class _Info(C.Structure):
 class Totals:
     matches: int
     newlines: int
-    long_lines: int
+    flags: int
     kernel_ms: float
     launches: int
     kernel: str = "none"
@@ -160,7 +160,7 @@ class Scanner:
         _check(lib().ugx_scanner_set_option(self._h, name.encode(), int(value)))
 
     def _totals(self, t: _Totals) -> Totals:
-        return Totals(t.matches, t.newlines, t.long_lines, t.kernel_ms, t.launches,
+        return Totals(t.matches, t.newlines, t.flags, t.kernel_ms, t.launches,
                       lib().ugx_kernel_name(t.kernel).decode())
 
     def count_lines(self, pattern: Pattern, data) -> Totals:
@@ -313,7 +313,7 @@ class Sharded:
         if rc != 0:
             raise UgxError(rc, lib().ugx_sharded_last_error().decode("utf-8", "replace"))
         info = [{f: getattr(sh, f) for f, _ in _Shard._fields_ if not f.startswith("reserved")} for sh in shards]
-        tot = Totals(t.matches, t.newlines, t.long_lines, t.kernel_ms, t.launches, lib().ugx_kernel_name(t.kernel).decode())
+        tot = Totals(t.matches, t.newlines, t.flags, t.kernel_ms, t.launches, lib().ugx_kernel_name(t.kernel).decode())
         return tot, (out[:cnt.value] if out is not None else None), info
 
     def close(self):

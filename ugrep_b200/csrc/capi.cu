@@ -642,6 +642,7 @@ int scan_spans(ugx_scanner* s, const ugx_pattern* p, const uint8_t* dbuf, uint64
   }
   tt->matches = nrec;
   tt->newlines = s->h_totals[1];
+  tt->flags |= UGX_TOT_NEWLINES;
   tt->kernel = UGX_K_SPAN;
   *valid = true;
   return UGX_OK;
@@ -699,6 +700,7 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
     float ms0 = 0;
     CU(cudaEventElapsedTime(&ms0, s->ev0, s->ev1));
     tt.newlines = s->h_totals[1];
+    tt.flags |= UGX_TOT_NEWLINES;
     tt.kernel_ms = ms0;
     tt.launches = 1;
     tt.kernel = UGX_K_NEWLINES;
@@ -734,6 +736,7 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
       return UGX_OK;
     }
     tt.launches = 0; // the line-at-a-time kernels take over
+    tt.flags |= UGX_TOT_SPAN_HANDOVER;
   }
   const uint64_t tile_bytes = ugx::scan_tile_bytes(p->dev);
   const uint64_t ntiles = (n + tile_bytes - 1) / tile_bytes;
@@ -920,6 +923,8 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
   CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
   tt.matches = s->h_totals[0];
   tt.newlines = s->h_totals[1];
+  if (!stream_route || s->count_newlines)
+    tt.flags |= UGX_TOT_NEWLINES;
   tt.kernel_ms = ms;
   if (totals)
     *totals = tt;
@@ -1188,6 +1193,7 @@ int ugx_count_newlines(ugx_scanner* s, const void* buf, uint64_t nbytes, ugx_tot
     tt.launches = 1;
     tt.kernel = UGX_K_NEWLINES;
   }
+  tt.flags |= UGX_TOT_NEWLINES;
   if (totals)
     *totals = tt;
   return UGX_OK;

@@ -172,7 +172,7 @@ int ugx_sharded_scan(ugx_sharded* s, const void* host_buf, uint64_t n, int mode,
     {
       rcs[r] = mode == UGX_MODE_LINES ? ugx_count_lines(s->scanners[r], s->patterns[r], buf + cuts[r], len, &tt[r])
                                       : ugx_count_matches(s->scanners[r], s->patterns[r], buf + cuts[r], len, &tt[r]);
-      if (rcs[r] == UGX_OK && mode == UGX_MODE_LINES && tt[r].newlines == 0)
+      if (rcs[r] == UGX_OK && (tt[r].flags & UGX_TOT_NEWLINES) == 0)
       {
         // the streaming `-c` kernels only count newlines on request: the bases of later shards want them
         ugx_totals nl;
@@ -270,10 +270,12 @@ int ugx_sharded_scan(ugx_sharded* s, const void* host_buf, uint64_t n, int mode,
   if (totals != nullptr)
   {
     memset(totals, 0, sizeof(*totals));
+    totals->flags = UGX_TOT_NEWLINES;
     for (int r = 0; r < nd; ++r)
     {
       totals->matches += tt[r].matches;
       totals->newlines += tt[r].newlines;
+      totals->flags |= tt[r].flags & UGX_TOT_SPAN_HANDOVER;
       totals->launches += tt[r].launches;
       if (tt[r].kernel_ms > totals->kernel_ms)
         totals->kernel_ms = tt[r].kernel_ms; // the devices run side by side: the slowest one

@@ -233,6 +233,8 @@ struct DfaEval {
   ViaTables via;        // k-gram viability of an attempt: a survivor that cannot start a match is dropped before stage 2
   mutable uint32_t via_tick = 0; // spans with survivors seen so far; every 64th measures what the table spares ...
   mutable bool via_keep = true;  // ... and the next 63 use it only if that is worth its two lookups per byte
+  mutable bool via_first = false; // the table alone picks the survivors (it is at least as selective as the prefilter's
+                                  // first-stage planes, which are then not evaluated at all; stage 2 stays exact)
 
   __device__ __forceinline__ void try_at(uint64_t sbase, uint32_t off, bool exact) const
   {
@@ -245,6 +247,20 @@ struct DfaEval {
     const bool interior = sbase + SC_SPAN + 24 <= t.end; // uniform
     uint32_t surv = 0;
     bool exact;
+    if (via.on && interior && via_first && (via_tick & 63u) != 0)
+    {
+      ++via_tick;
+      exact = false;
+      Window W;
+#pragma unroll
+      for (int i = 0; i < 7; ++i)
+        W.w[i] = w[i];
+      surv = viable16(via, W);
+      if (!__any_sync(0xffffffffu, surv != 0))
+        return false;
+    }
+    else
+    {
     if (h4 != nullptr && !pm2 && interior)
     {
       // hashed-predictor terms: one rolling 12-bit hash and one lookup per text byte.  Byte i of the predictor
@@ -343,11 +359,17 @@ struct DfaEval {
           W.w[i] = w[i];
         const uint32_t v = viable16(via, W);
         if (probe)
-          via_keep = __reduce_add_sync(0xffffffffu, __popc(surv & ~v)) >= 32u;
+        {
+          const uint32_t spared = __reduce_add_sync(0xffffffffu, __popc(surv & ~v));
+          const uint32_t extra = __reduce_add_sync(0xffffffffu, __popc(v & ~surv));
+          via_keep = spared >= 32u;
+          via_first = via_keep && !exact && extra <= 16u; // the table alone would hand stage 2 at most 16 more
+        }
         surv &= v;
         if (!__any_sync(0xffffffffu, surv != 0))
           return false;
       }
+    }
     }
     // ---- compaction + balanced stage 2.  Per round: a warp scan of the lanes' survivor counts; the lanes whose
     // survivors fit into the free part of the 64-entry queue write ALL of them (so a lane holding a run of
