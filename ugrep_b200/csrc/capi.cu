@@ -130,6 +130,8 @@ struct ugx_scanner {
   // span scan scratch
   uint64_t* span_regions = nullptr; // [5 * regions]
   uint64_t span_regions_cap = 0;
+  uint16_t* span_sel = nullptr;   // records: selected match starts per 16-byte chunk
+  uint64_t span_sel_cap = 0;
   uint64_t* batch = nullptr;      // ugx_count_batch: file table, counters, tile table
   uint64_t batch_cap = 0;
   bool no_span = false;           // counting matches / records take the line-at-a-time kernels (A/B timing, tests)
@@ -502,6 +504,7 @@ void ugx_scanner_destroy(ugx_scanner* s)
   cudaFreeHost(s->h_totals);
   cudaFree(s->region_sum);
   cudaFree(s->span_regions);
+  cudaFree(s->span_sel);
   cudaFree(s->batch);
   cudaFree(s->tile_base);
   cudaFree(s->rec_stage);
@@ -602,6 +605,8 @@ int scan_spans(ugx_scanner* s, const ugx_pattern* p, const uint8_t* dbuf, uint64
   *valid = false;
   const uint64_t nreg = ugx::stream_regions(n);
   int rc = ensure(s->span_regions, s->span_regions_cap, 5 * nreg + 8);
+  if (rc == UGX_OK && want_records)
+    rc = ensure(s->span_sel, s->span_sel_cap, (n + 15) / 16 + 64);
   if (rc != UGX_OK)
     return rc;
   ugx::SpanArgs a;
@@ -611,6 +616,7 @@ int scan_spans(ugx_scanner* s, const ugx_pattern* p, const uint8_t* dbuf, uint64
   a.reg_emain = s->span_regions + 2 * nreg;
   a.reg_elast = s->span_regions + 3 * nreg;
   a.reg_v = s->span_regions + 4 * nreg;
+  a.sel_bits = want_records ? s->span_sel : nullptr;
   a.base_offset = base_offset;
   a.base_line = base_line;
   a.tail = reinterpret_cast<const uint64_t*>(s->totals + 5);

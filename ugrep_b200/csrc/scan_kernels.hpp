@@ -99,6 +99,7 @@ struct SpanArgs {
   uint64_t* reg_emain;     // [regions] farthest end of a success that starts in spans 0..30 of the region
   uint64_t* reg_elast;     // [regions] ... in its last span (the next region's window)
   uint64_t* reg_v;         // [regions] validation point of the region's chain start (~0 = none needed)
+  uint16_t* sel_bits;      // [ceil(n / 16) + 32] or nullptr: the selected match starts of every 16-byte chunk (records)
   ugx_match* out;          // emit pass: records in input order
   uint64_t out_cap;
   uint64_t base_offset, base_line;

@@ -44,6 +44,7 @@
 #include "line_match.cuh"
 #include "ptx.cuh"
 #include "scan_kernels.hpp"
+#include "stream_common.cuh"
 #include "tile_phase_a.cuh"
 #include "viability.cuh"
 
@@ -211,9 +212,9 @@ __global__ void __launch_bounds__(32) last_line_kernel(const uint8_t* __restrict
     tail[0] = t0;
 }
 
-// EMIT false: per region {matches that start in it, newlines in it, farthest match ends, validation point};
-// EMIT true:  the same walk writing records; reg_matches / reg_newlines then hold the exclusive prefixes
-template <bool EMIT, int THREADS>
+// per region: {matches that start in it, newlines in it, farthest match ends, validation point}; with a.sel_bits, also
+// the selected match starts of every chunk (16 bits per 16 text bytes) for span_emit_kernel
+template <int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 1 : 4)
 span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, SpanArgs a)
 {
@@ -269,12 +270,6 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
     int64_t cursor = 0;               // chain cursor, relative to the current span's base (warp-uniform)
     uint64_t far_base = 0;            // look-ahead cache: the carry out of the run that ends in the span at far_base
     uint32_t far_val = 0;
-    uint64_t out_base = 0, line_base = 0;
-    if (EMIT)
-    {
-      out_base = a.reg_matches[r];
-      line_base = a.reg_newlines[r] + 1 + a.base_line;
-    }
     // masks of the first span to process (the window before the region, or span 0 of region 0) and of the one after
     int s = r == 0 ? 0 : -1;
     // The viability table costs two lookups per byte.  The lazy form lives on it; the mask form measures on the first
@@ -551,52 +546,15 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
           else
             emain = fe > emain ? fe : emain;
         }
-        if (EMIT)
-        {
-          // record index and line number of every selected match
-          uint32_t mi = nsel, ni = __popc(cur.nl);
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1)
-          {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, mi, d), z = __shfl_up_sync(0xffffffffu, ni, d);
-            if (lane >= static_cast<uint32_t>(d))
-            {
-              mi += y;
-              ni += z;
-            }
-          }
-          const uint32_t mtot = __shfl_sync(0xffffffffu, mi, 31), ntot = __shfl_sync(0xffffffffu, ni, 31);
-          uint64_t idx = out_base + m_run + (mi - nsel);
-          const uint64_t lno = line_base + nl_run + (ni - __popc(cur.nl));
-          uint32_t m = sel;
-          while (m != 0)
-          {
-            const uint32_t k = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t d = dtab[lane * 16 + k];
-            ugx_match rec;
-            rec.line = lno + __popc(cur.nl & ((1u << k) - 1u));
-            rec.offset = sbase + lane * 16 + k + a.base_offset;
-            rec.len = d & 0xffffu;
-            rec.cap = d >> 16;
-            if (idx < a.out_cap)
-              a.out[idx] = rec;
-            ++idx;
-          }
-          m_run += mtot;
-          nl_run += ntot;
-        }
-        else
-        {
-          m_run += nsel;            // lane-private here; reduced after the region
-          nl_run += __popc(cur.nl);
-        }
+        m_run += nsel;            // lane-private; reduced after the region
+        nl_run += __popc(cur.nl);
+        if (a.sel_bits != nullptr)
+          a.sel_bits[(sbase >> 4) + lane] = static_cast<uint16_t>(sel);
       }
       __syncwarp(); // dtab / queue are rewritten by the next span
       cursor -= SP_SPAN;
       cur = nxt;
     }
-    if (!EMIT)
     {
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1)
@@ -619,6 +577,115 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
   }
   if (bad != 0)
     atomicOr(a.flags, bad);
+}
+
+// one anchored attempt for a known match start: (accept << 16) | length of the longest match
+__device__ __forceinline__ uint32_t longest_at(const Text& t, const DevPattern& P, const Tables& T, uint64_t pos)
+{
+  if (P.one)
+    return (1u << 16) | P.len;
+  uint32_t state = 0, best = 0;
+  uint64_t p = pos;
+  for (;;)
+  {
+    if (p >= t.end)
+      break;
+    const uint32_t nx = T.next[state * P.ncls + T.cls[t.raw(p++)]];
+    if (nx == D_DEAD)
+      break;
+    if (nx >= P.first_acc)
+    {
+      const uint32_t acc = __ldg(P.accept + nx);
+      if ((acc & 0x7fffffffu) != 0)
+        best = ((acc & 0x7fffu) << 16) | static_cast<uint32_t>((p - pos) & 0xffffu);
+      if (acc & 0x80000000u)
+        break;
+    }
+    state = nx;
+  }
+  return best;
+}
+
+// the records: span_scan_kernel left the selected match starts of every chunk in a.sel_bits and the final kernel turned
+// the regions' counts into prefixes, so this pass only reads the text for its newlines (line numbers), re-runs the DFA
+// at the few selected positions for length and accept index, and writes every record to its final place — input
+// order, no atomics, no reorder pass.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 1 : 4)
+span_emit_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, SpanArgs a)
+{
+  constexpr uint32_t NWARPS = THREADS / 32;
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  uint8_t* s_cls = smem;
+  uint8_t* s_pred = s_cls + 256;
+  uint8_t* s_tap = s_pred + UGX_HASH;
+  uint16_t* s_next = reinterpret_cast<uint16_t*>(s_tap + UGX_BTAP);
+  stage_tables_bulk(&s_bar, s_cls, P.cls, s_pred, P.pred, s_tap, P.tap, s_next, P.next,
+                    a.stage_table ? ((P.table_bytes + 15) / 16) * 16 : 0);
+  __syncthreads();
+  Tables T;
+  T.cls = s_cls;
+  T.pred = s_pred;
+  T.tap = s_tap;
+  T.next = a.stage_table ? s_next : P.next;
+  const Text t{buf, n};
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint64_t limit = __ldcg(a.tail);
+  const uint64_t nregions = (limit + SC_REGION - 1) / SC_REGION;
+  const uint64_t total_warps = static_cast<uint64_t>(gridDim.x) * NWARPS;
+  for (uint64_t r = static_cast<uint64_t>(blockIdx.x) * NWARPS + wid; r < nregions; r += total_warps)
+  {
+    const uint64_t rb = r * SC_REGION;
+    uint64_t idx0 = a.reg_matches[r];
+    uint64_t line0 = a.reg_newlines[r] + 1 + a.base_line;
+    for (int s = 0; s < SP_SPANS; ++s)
+    {
+      const uint64_t sbase = rb + static_cast<uint64_t>(s) * SP_SPAN;
+      if (sbase >= limit)
+        break;
+      const uint64_t base = sbase + lane * 16;
+      uint32_t nl = 0, sel = 0;
+      if (base < limit)
+      {
+        const uint4 v = load_chunk_guarded(buf, n, base);
+        nl = newline_mask_exact4(v.x, v.y, v.z, v.w);
+        if (base + 16 > limit)
+          nl &= (1u << (limit - base)) - 1u;
+        sel = a.sel_bits[(sbase >> 4) + lane];
+      }
+      const uint32_t nsel = __popc(sel), nnl = __popc(nl);
+      uint32_t mi = nsel, ni = nnl;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, mi, d), z = __shfl_up_sync(0xffffffffu, ni, d);
+        if (lane >= static_cast<uint32_t>(d))
+        {
+          mi += y;
+          ni += z;
+        }
+      }
+      uint64_t idx = idx0 + (mi - nsel);
+      const uint64_t lno = line0 + (ni - nnl);
+      while (sel != 0)
+      {
+        const uint32_t k = __ffs(sel) - 1;
+        sel &= sel - 1;
+        const uint32_t d = longest_at(t, P, T, base + k);
+        ugx_match rec;
+        rec.line = lno + __popc(nl & ((1u << k) - 1u));
+        rec.offset = base + k + a.base_offset;
+        rec.len = d & 0xffffu;
+        rec.cap = d >> 16;
+        if (idx < a.out_cap)
+          a.out[idx] = rec;
+        ++idx;
+      }
+      idx0 += __shfl_sync(0xffffffffu, mi, 31);
+      line0 += __shfl_sync(0xffffffffu, ni, 31);
+    }
+  }
 }
 
 // one CTA: exclusive prefixes of the regions' match / newline counts, the validation of the regions' chain starts,
@@ -791,7 +858,7 @@ template <bool EMIT, int THREADS>
 static cudaError_t launch_span_one(const DevPattern& P, const uint8_t* buf, uint64_t n, SpanArgs a, size_t smem, int sm_count,
                                    cudaStream_t st)
 {
-  auto kern = span_scan_kernel<EMIT, THREADS>;
+  auto kern = EMIT ? span_emit_kernel<THREADS> : span_scan_kernel<THREADS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, UGX_MAX_DYN_SMEM);
   if (e != cudaSuccess)
     return e;
@@ -825,7 +892,8 @@ cudaError_t launch_span_scan(const DevPattern& P, const uint8_t* buf, uint64_t n
   const bool use_via = P.via_k != 0 && span_smem_bytes(P, false, true, threads) <= static_cast<size_t>(UGX_MAX_DYN_SMEM);
   const bool stage = P.table_bytes <= 160 * 1024 &&
                      span_smem_bytes(P, true, use_via, threads) <= static_cast<size_t>(UGX_MAX_DYN_SMEM);
-  const size_t smem = span_smem_bytes(P, stage, use_via, threads);
+  const size_t smem = emit ? 256 + UGX_HASH + UGX_BTAP + (stage ? ((P.table_bytes + 15) / 16) * 16 : 0)
+                           : span_smem_bytes(P, stage, use_via, threads);
   a.stage_table = stage ? 1u : 0u;
   a.use_via = use_via ? 1u : 0u;
 #define UGX_SPAN_GO(EMITF)                                                        \
