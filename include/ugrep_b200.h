@@ -171,6 +171,13 @@ int  ugx_abi_version(void);
 int  ugx_pattern_create(const uint32_t *opc, uint32_t nop, const ugx_prefilter *pf,
                         uint32_t matcher_flags, int device, ugx_pattern **out);
 int  ugx_pattern_load(const char *path, int device, ugx_pattern **out);
+/* host only: the compiled form of ONE fixed string (`ugrep -F 'literal'`): the opcode words and prefilter fields the
+ * reference's pattern compiler produces for it (lib/pattern.cpp:2823-3063, 4286-4340, 510-598), byte for byte, so that
+ * a literal search needs no reference binary.  *nop receives the word count (UGX_E_OVERFLOW when cap is too small);
+ * UGX_E_UNSUPPORTED for an empty literal, 255 bytes or more, or one that holds NUL / CR / LF.  The general regex and
+ * word-list compiler is not part of this library. */
+int  ugx_compile_literal(const uint8_t *literal, uint32_t len, uint32_t *opc, uint32_t cap, uint32_t *nop,
+                         ugx_prefilter *pf);
 /* host only (no device needed): DFA export + filter plan of a compiled pattern */
 int  ugx_plan_describe(const uint32_t *opc, uint32_t nop, const ugx_prefilter *pf, uint32_t matcher_flags,
                        ugx_plan_info *out);

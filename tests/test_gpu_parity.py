@@ -434,6 +434,25 @@ def test_span_kernels_hand_over_what_they_cannot_vouch_for(gpu):
     sc.set_option("count_newlines", 0)
 
 
+def test_literal_compiled_by_the_library_itself(gpu):
+    """config 1 without any reference binary: ugx_compile_literal + ugx_pattern_create, against the oracle running
+    the reference-compiled pattern"""
+    api, sc = gpu
+    data = corpus.block("c1", 4 << 20)
+    op = O.OraclePattern(os.path.join(PAT_DIR, "c1.ugxp"))
+    pat = api.Pattern.literal(b"Sherlock Holmes", 0)
+    t = sc.count_lines(pat, data)
+    assert t.matches == op.count_lines(data) and t.kernel == "count_lines_literal_kernel"
+    rec, _ = sc.find_all(pat, data)
+    assert same(rec, op.find_all(data))
+    for lit in (b"the", b"e", b"water long little", "naïve".encode()):
+        pat = api.Pattern.literal(lit, 0)
+        blk = corpus.block("c4" if lit[0] > 127 or b"\xc3" in lit else "c1", 1 << 20)
+        raw = blk.tobytes()
+        assert sc.count_matches(pat, blk).matches == raw.count(lit), lit   # non-overlapping occurrences
+        assert sc.count_lines(pat, blk).matches == sum(1 for ln in raw.split(b"\n") if lit in ln), lit
+
+
 def test_scanners_on_two_host_threads_share_a_pattern(gpu):
     """a ugx_pattern is shareable, a ugx_scanner belongs to one host thread: two threads scanning at once with
     different patterns (different table sizes, hence different shared-memory needs of the same kernels)"""

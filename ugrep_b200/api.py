@@ -27,7 +27,7 @@ ADVANCE_NAMES = ["none", "pin1_one", "pin1_pma", "pin1_pmh", "pin_one", "pin_pma
 
 EXPORTS = ["ugx_last_error", "ugx_kernel_name", "ugx_plan_describe", "ugx_abi_version", "ugx_pattern_create", "ugx_pattern_load", "ugx_pattern_info_get",
            "ugx_pattern_destroy", "ugx_scanner_create", "ugx_scanner_destroy", "ugx_count_lines", "ugx_count_matches",
-           "ugx_viability_describe", "ugx_check_text", "ugx_count_batch", "ugx_sharded_create", "ugx_sharded_destroy", "ugx_sharded_set_option", "ugx_sharded_scan", "ugx_sharded_last_error", "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_scanner_set_option", "ugx_count_newlines"]
+           "ugx_viability_describe", "ugx_check_text", "ugx_compile_literal", "ugx_count_batch", "ugx_sharded_create", "ugx_sharded_destroy", "ugx_sharded_set_option", "ugx_sharded_scan", "ugx_sharded_last_error", "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_scanner_set_option", "ugx_count_newlines"]
 
 
 class UgxError(RuntimeError):
@@ -115,6 +115,22 @@ def _buffer(data):
     return a.ctypes.data, a.size, a
 
 
+PREFILTER_BYTES = 12 * 4 + 256 + 256 + 2048 + 4096 + 4096 + 32 + 32 + 256
+
+
+def compile_literal(text: bytes):
+    """(opcode words, ugx_prefilter bytes) of one fixed string, as the reference's compiler would produce them"""
+    L = lib()
+    L.ugx_compile_literal.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p]
+    opc = np.zeros(2 * (len(text) + 1) + 2, dtype=np.uint32)
+    nop = C.c_uint32()
+    pf = C.create_string_buffer(PREFILTER_BYTES)
+    rc = L.ugx_compile_literal(bytes(text), len(text), opc.ctypes.data, len(opc), C.byref(nop), pf)
+    if rc != 0:
+        raise UgxError(rc, "ugx_compile_literal: literal outside its scope" if rc == 2 else "ugx_compile_literal failed")
+    return opc[:nop.value].copy(), pf.raw
+
+
 class Pattern:
     """A compiled pattern uploaded to one device (immutable, shareable)."""
 
@@ -126,6 +142,14 @@ class Pattern:
     def load(cls, path: str, device: int = 0) -> "Pattern":
         h = C.c_void_p()
         _check(lib().ugx_pattern_load(os.fsencode(path), device, C.byref(h)))
+        return cls(h, device)
+
+    @classmethod
+    def literal(cls, text: bytes, device: int = 0) -> "Pattern":
+        """`ugrep -F TEXT`: compiled by the library itself (ugx_compile_literal), no reference binary needed"""
+        opc, pf = compile_literal(text)
+        h = C.c_void_p()
+        _check(lib().ugx_pattern_create(opc.ctypes.data, len(opc), pf, 0, device, C.byref(h)))
         return cls(h, device)
 
     @property
