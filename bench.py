@@ -341,7 +341,8 @@ def main():
         e2e = {"value": round(world * nbytes * esteps / dt / 1e9, 3), "unit": "GB/s",
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 32, "steps": esteps, "host_memory": "pinned"}
         del host, hb
-        # the same from ordinary pageable memory (what an mmap'ing caller hands over without registering it)
+        # the same from ordinary pageable memory (what an mmap'ing caller hands over without registering it): the
+        # library's feeder threads copy it through pinned slots (capi.cu feed_pageable)
         pg = np.empty(nbytes, dtype=np.uint8)
         for i in range(reps):
             pg[i * block.size:(i + 1) * block.size] = block

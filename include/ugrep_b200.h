@@ -201,6 +201,7 @@ void ugx_scanner_destroy(ugx_scanner *s);
  *   "match_lines"     counting takes the position-parallel-attempt kernel (match_lines.cu) instead of the line scan
  *   "two_pass_records" records by a count pass + an emit pass instead of the single-pass staging form
  *   "no_pipeline"     host buffers: one copy, then the scan (default: chunked copy overlapped with the scan)
+ *   "no_feeder"       pageable host buffers take one plain cudaMemcpyAsync instead of the feeder threads
  *   "no_span"         counting matches / records take the line-at-a-time kernels instead of the span kernels */
 int  ugx_scanner_set_option(ugx_scanner *s, const char *name, int value);
 

@@ -69,7 +69,7 @@ PATTERNS = [
 # output modes of Grep::search (src/ugrep.cpp:10346-13276) that go through match(FIND)
 MODES = [["-c"], ["-c", "-o"], ["-o"], ["-o", "-n"], ["-o", "-n", "-k", "-b", "-T"], ["-n"], [], ["-n", "-k", "-b", "-T"],
          ["-v", "-c"], ["-v", "-n"], ["-l"], ["-q"], ["-C2", "-n"], ["-A1"], ["-B1", "-n"], ["-m2", "-n"], ["-y", "-n"],
-         ["--mmap", "-n", "-b", "-o"], ["--mmap", "-c"]]
+         ["--mmap", "-n", "-b", "-o"], ["--mmap", "-c"], ["-x", "-c"], ["-w", "-n"]]
 
 
 def _cases():

@@ -265,12 +265,20 @@ def test_pipelined_host_buffer_equals_device_scan(gpu):
             host = host.copy()
             host[at:at + 15] = np.frombuffer(b"Sherlock Holmes", dtype=np.uint8)
         want_dev = sc.count_lines(pat, torch.from_numpy(host).cuda())
-        got = sc.count_lines(pat, host)
-        assert got.launches >= 3, got
+        pinned = torch.from_numpy(host).pin_memory()
+        got = sc.count_lines(pat, pinned.numpy())
+        assert got.launches >= 3, got          # page-locked memory: chunked copy overlapped with the scan
         assert got.matches == want_dev.matches
         sc.set_option("no_pipeline", 1)
-        assert sc.count_lines(pat, host).matches == want_dev.matches
+        assert sc.count_lines(pat, pinned.numpy()).matches == want_dev.matches
         sc.set_option("no_pipeline", 0)
+        # pageable memory (what ugrep hands over): feeder threads through pinned slots, then one launch
+        got = sc.count_lines(pat, host)
+        assert got.launches == 1 and got.matches == want_dev.matches
+        sc.set_option("no_feeder", 1)
+        assert sc.count_lines(pat, host).matches == want_dev.matches
+        sc.set_option("no_feeder", 0)
+        assert sc.count_matches(pat, host).matches == sc.count_matches(pat, pinned.numpy()).matches
         if pname == "c2":
             assert got.matches == reps * op.count_lines(block)
 

@@ -8,6 +8,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -130,6 +131,11 @@ struct ugx_scanner {
   // span scan scratch
   uint64_t* span_regions = nullptr; // [5 * regions]
   uint64_t span_regions_cap = 0;
+  // pageable host buffers: feeder threads copy chunks into pinned slots, each slot goes to the device on its thread's stream
+  std::vector<uint8_t*> feed_slots;      // [2 * feed_threads] pinned, FEED_CHUNK bytes each
+  std::vector<cudaStream_t> feed_streams; // [feed_threads]
+  std::vector<cudaEvent_t> feed_events;   // [2 * feed_threads] slot free again
+  bool no_feeder = false;         // pageable buffers take one plain cudaMemcpyAsync (A/B timing)
   uint16_t* span_sel = nullptr;   // records: selected match starts per 16-byte chunk
   uint64_t span_sel_cap = 0;
   uint64_t* batch = nullptr;      // ugx_count_batch: file table, counters, tile table
@@ -505,6 +511,12 @@ void ugx_scanner_destroy(ugx_scanner* s)
   cudaFree(s->region_sum);
   cudaFree(s->span_regions);
   cudaFree(s->span_sel);
+  for (uint8_t* p : s->feed_slots)
+    cudaFreeHost(p);
+  for (cudaEvent_t e : s->feed_events)
+    cudaEventDestroy(e);
+  for (cudaStream_t st : s->feed_streams)
+    cudaStreamDestroy(st);
   cudaFree(s->batch);
   cudaFree(s->tile_base);
   cudaFree(s->rec_stage);
@@ -549,6 +561,83 @@ int ensure(T*& ptr, uint64_t& cap, uint64_t need)
   return UGX_OK;
 }
 
+constexpr uint64_t FEED_CHUNK = 8ull << 20; // bytes per pinned slot of the pageable feeder
+constexpr uint64_t FEED_MIN = 32ull << 20;  // smaller pageable buffers take one plain copy
+
+// Host-to-device copy of a PAGEABLE buffer (what an mmap'ing caller such as ugrep hands over).  cudaMemcpyAsync from
+// pageable memory goes through the driver's own staging at ~10 GB/s on this box; here K host threads copy 8 MiB chunks
+// into pinned slots (two per thread) and send each slot on the thread's own stream, so the memcpy's of some chunks
+// overlap the DMA of others.  The scan stream waits on every thread's last copy.
+int feed_pageable(ugx_scanner* s, uint8_t* dst, const uint8_t* src, uint64_t n)
+{
+  if (s->feed_streams.empty())
+  {
+    // half the host threads, shared between the ranks of this box when there are several (torchrun's LOCAL_WORLD_SIZE)
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned ranks = 1;
+    if (const char* lws = getenv("LOCAL_WORLD_SIZE"))
+      ranks = static_cast<unsigned>(atoi(lws)) > 0 ? static_cast<unsigned>(atoi(lws)) : 1;
+    unsigned k = hw / (2 * ranks);
+    if (const char* env = getenv("UGX_FEED_THREADS"))
+      k = static_cast<unsigned>(atoi(env));
+    if (k < 2)
+      k = 2;
+    if (k > 8)
+      k = 8;
+    for (unsigned i = 0; i < k; ++i)
+    {
+      cudaStream_t st = nullptr;
+      CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      s->feed_streams.push_back(st);
+      for (int j = 0; j < 2; ++j)
+      {
+        void* p = nullptr;
+        CU(cudaHostAlloc(&p, FEED_CHUNK, cudaHostAllocDefault));
+        s->feed_slots.push_back(static_cast<uint8_t*>(p));
+        cudaEvent_t ev = nullptr;
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        s->feed_events.push_back(ev);
+      }
+    }
+  }
+  const unsigned K = static_cast<unsigned>(s->feed_streams.size());
+  const uint64_t nchunks = (n + FEED_CHUNK - 1) / FEED_CHUNK;
+  std::vector<cudaError_t> errs(K, cudaSuccess);
+  std::vector<std::thread> workers;
+  for (unsigned w = 0; w < K; ++w)
+    workers.emplace_back([&, w]() {
+      cudaError_t e = cudaSetDevice(s->device);
+      uint64_t round = 0;
+      for (uint64_t c = w; c < nchunks && e == cudaSuccess; c += K, ++round)
+      {
+        const unsigned slot = 2 * w + static_cast<unsigned>(round & 1);
+        if (round >= 2)
+          e = cudaEventSynchronize(s->feed_events[slot]); // the slot's previous copy has left it
+        if (e != cudaSuccess)
+          break;
+        const uint64_t off = c * FEED_CHUNK;
+        const uint64_t len = n - off < FEED_CHUNK ? n - off : FEED_CHUNK;
+        memcpy(s->feed_slots[slot], src + off, len);
+        e = cudaMemcpyAsync(dst + off, s->feed_slots[slot], len, cudaMemcpyHostToDevice, s->feed_streams[w]);
+        if (e == cudaSuccess)
+          e = cudaEventRecord(s->feed_events[slot], s->feed_streams[w]);
+      }
+      errs[w] = e;
+    });
+  for (auto& t : workers)
+    t.join();
+  for (unsigned w = 0; w < K; ++w)
+    if (errs[w] != cudaSuccess)
+      return cuda_fail(errs[w], "pageable feeder");
+  // the scan stream continues after the last copy of every feeder stream
+  for (unsigned w = 0; w < K; ++w)
+  {
+    CU(cudaEventRecord(s->ev_copy, s->feed_streams[w]));
+    CU(cudaStreamWaitEvent(s->stream, s->ev_copy, 0));
+  }
+  return UGX_OK;
+}
+
 // make `buf` visible to the device: device pointers are used in place, host pointers are staged
 int resolve(ugx_scanner* s, const void* buf, uint64_t n, const uint8_t** dev, uint64_t* h2d)
 {
@@ -575,7 +664,17 @@ int resolve(ugx_scanner* s, const void* buf, uint64_t n, const uint8_t** dev, ui
   int rc = ensure(s->stage, s->stage_cap, n + 16);
   if (rc != UGX_OK)
     return rc;
-  CU(cudaMemcpyAsync(s->stage, buf, n, cudaMemcpyHostToDevice, s->stream));
+  const bool pageable = e != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
+  if (pageable && n >= FEED_MIN && !s->no_feeder)
+  {
+    // earlier work on the scan stream may still read the staging buffer
+    CU(cudaStreamSynchronize(s->stream));
+    rc = feed_pageable(s, s->stage, static_cast<const uint8_t*>(buf), n);
+    if (rc != UGX_OK)
+      return rc;
+  }
+  else
+    CU(cudaMemcpyAsync(s->stage, buf, n, cudaMemcpyHostToDevice, s->stream));
   *dev = s->stage;
   *h2d = n;
   return UGX_OK;
@@ -593,6 +692,19 @@ bool is_host_pointer(const void* buf)
     return true;
   }
   return at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged;
+}
+
+// page-locked host memory (cudaHostAlloc / cudaHostRegister): DMA reads it directly
+bool is_pinned_host_pointer(const void* buf)
+{
+  cudaPointerAttributes at;
+  const cudaError_t e = cudaPointerGetAttributes(&at, buf);
+  if (e != cudaSuccess)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
 }
 
 // `ugrep -c -o` / `ugrep -o -n -b` through the span kernels (span_scan.cu).  *valid = false: the spans could not vouch
@@ -683,7 +795,9 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
   // a host buffer on the streaming route is copied chunk by chunk, overlapped with the scan, when every read of a
   // scanned position stays within one region of it: pure literals, and DFAs whose longest match is bounded
   const bool bounded = ugx::count_lines_literal_eligible(p->dev) || p->dfa.max_match_len < ugx::SC_REGION - 512;
-  const bool pipelined = stream_route && bounded && !p->never && !s->no_pipeline && n >= 2 * PIPE_CHUNK && is_host_pointer(buf);
+  // (chunk-wise overlap of copy and scan for page-locked buffers; pageable ones go through the feeder threads of resolve())
+  const bool pipelined = stream_route && bounded && !p->never && !s->no_pipeline && n >= 2 * PIPE_CHUNK && is_host_pointer(buf) &&
+                         (is_pinned_host_pointer(buf) || s->no_feeder);
   int rc;
   if (pipelined)
   {
@@ -1028,6 +1142,11 @@ int ugx_scanner_set_option(ugx_scanner* s, const char* name, int value)
   if (strcmp(name, "stream_dfa") == 0)
   {
     s->stream_dfa = value != 0;
+    return UGX_OK;
+  }
+  if (strcmp(name, "no_feeder") == 0)
+  {
+    s->no_feeder = value != 0;
     return UGX_OK;
   }
   if (strcmp(name, "no_span") == 0)
