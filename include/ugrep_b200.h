@@ -178,6 +178,13 @@ int  ugx_pattern_load(const char *path, int device, ugx_pattern **out);
  * word-list compiler is not part of this library. */
 int  ugx_compile_literal(const uint8_t *literal, uint32_t len, uint32_t *opc, uint32_t cap, uint32_t *nop,
                          ugx_prefilter *pf);
+/* host only: the same for a LIST of fixed strings (`ugrep -F -f words.txt`, `-F -e A -e B`; accept index = 1-based
+ * position in the list): the tree DFA's opcode words and the needle / bitap / hashed-predictor tables, byte for byte
+ * what the reference compiles (lib/pattern.cpp:798-866, 3812-4639, 331-598, 2764-3063).  UGX_E_UNSUPPORTED: an empty
+ * string, NUL / CR / LF in a string, or a list for which the reference's DFA analysis makes a cut (look-back search:
+ * that part of the analysis is not restated). */
+int  ugx_compile_words(const uint8_t *const *words, const uint32_t *lens, uint32_t nwords, uint32_t *opc, uint32_t cap,
+                       uint32_t *nop, ugx_prefilter *pf);
 /* host only (no device needed): DFA export + filter plan of a compiled pattern */
 int  ugx_plan_describe(const uint32_t *opc, uint32_t nop, const ugx_prefilter *pf, uint32_t matcher_flags,
                        ugx_plan_info *out);

@@ -461,6 +461,17 @@ def test_literal_compiled_by_the_library_itself(gpu):
         assert sc.count_lines(pat, blk).matches == sum(1 for ln in raw.split(b"\n") if lit in ln), lit
 
 
+def test_word_list_compiled_by_the_library_itself(gpu):
+    """config 2 without any reference binary: ugx_compile_words + ugx_pattern_create"""
+    api, sc = gpu
+    op = O.OraclePattern(os.path.join(PAT_DIR, "c2.ugxp"))
+    pat = api.Pattern.words(corpus.words_list(), 0)
+    for cname in ("c2", "c2s"):
+        data = corpus.block(cname, 4 << 20)
+        assert sc.count_lines(pat, data).matches == op.count_lines(data)
+        assert sc.count_matches(pat, data).matches == op.count_matches(data)
+
+
 def test_scanners_on_two_host_threads_share_a_pattern(gpu):
     """a ugx_pattern is shareable, a ugx_scanner belongs to one host thread: two threads scanning at once with
     different patterns (different table sizes, hence different shared-memory needs of the same kernels)"""

@@ -72,3 +72,73 @@ def test_literal_compile_equals_the_live_reference_on_random_literals(tmp_path):
             g = struct.unpack_from("<12I", got_pf, 0)
             print("MISMATCH", lit, f, g)
     assert bad == 0
+
+
+# ---- ugx_compile_words: `ugrep -F -f words.txt` (config 2)
+
+def test_wordlist_compile_equals_committed_reference_output():
+    """the config-2 pattern (1 000 words) and the three-literal golden, as the unmodified reference compiled them"""
+    from ugrep_b200 import corpus
+    pf, opc = parts(os.path.join(O.ROOT, "ugrep_b200", "patterns", "c2.ugxp"))
+    got_opc, got_pf = api.compile_words(corpus.words_list())
+    assert got_opc.tolist() == opc.tolist() and got_pf == pf
+    pf, opc = parts(G.pattern_path("alt3"))
+    got_opc, got_pf = api.compile_words([b"ERROR", b"WARN", b"INFO"])
+    assert got_opc.tolist() == opc.tolist() and got_pf == pf
+    # one word is one literal
+    a = api.compile_words([b"Sherlock Holmes"])
+    b = api.compile_literal(b"Sherlock Holmes")
+    assert a[0].tolist() == b[0].tolist() and a[1] == b[1]
+
+
+def test_wordlist_compile_scope():
+    for bad in ([b""], [b"ok", b""], [b"a\nb"], [b"a\x00"]):
+        with pytest.raises(api.UgxError) as e:
+            api.compile_words(bad)
+        assert e.value.code == 2
+
+
+def _random_lists():
+    from ugrep_b200 import corpus
+    rng = np.random.default_rng(5)
+    eng = [w.encode() for w in corpus._ENGLISH]
+    al = b"abcdefghijklmnopqrstuvwxyz0123456789"
+    for i in range(25):
+        yield [bytes(w) for w in rng.choice(eng, size=int(rng.integers(1, 60)), replace=False)]
+    for i in range(25):
+        yield corpus._syllable_words(np.random.default_rng(100 + i), int(rng.integers(2, 400)), int(rng.integers(1, 3)),
+                                     int(rng.integers(3, 7)), set())
+    for i in range(15):
+        pre = bytes(int(x) for x in rng.choice(list(b"abcdexyz"), size=int(rng.integers(1, 6))))
+        yield [pre + bytes(w) for w in rng.choice(eng, size=int(rng.integers(1, 30)), replace=False)]
+    for i in range(15):
+        yield sorted({bytes(int(x) for x in rng.choice(list(b"ab01"), size=int(rng.integers(1, 7)))) for _ in range(int(rng.integers(1, 40)))})
+    for i in range(25):
+        n, k, L = int(rng.integers(20, 500)), int(rng.integers(4, 36)), int(rng.integers(6, 14))
+        yield sorted({bytes(int(x) for x in rng.choice(list(al[:k]), size=int(rng.integers(max(1, L - 2), L + 1)))) for _ in range(n)})
+    yield corpus._syllable_words(np.random.default_rng(500), 9000, 3, 8, set())   # beyond 64K opcode words: LONG jumps
+    yield [w.encode() for w in ("naïve", "café", "über", "日本語", "Привет", "中文", "señor", "αβγ")]
+
+
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref (the built reference) is not present")
+def test_wordlist_compile_equals_the_live_reference_on_random_lists(tmp_path):
+    """byte equality of opcode words and prefilter block with `refscan dump -F -f`; a list the library refuses must be
+    one for which the reference's analysis cut the DFA (cut_ != 0), and only those"""
+    wf = tmp_path / "w.txt"
+    out = str(tmp_path / "p.ugxp")
+    n_ok = n_cut = 0
+    for words in _random_lists():
+        wf.write_bytes(b"\n".join(words) + b"\n")
+        O.ref_dump(["-F", "-f", str(wf)], out)
+        pf, opc = parts(out)
+        cut = struct.unpack_from("<12I", pf, 0)[11]
+        try:
+            got_opc, got_pf = api.compile_words(words)
+        except api.UgxError as e:
+            assert e.code == 2 and cut != 0, words[:3]
+            n_cut += 1
+            continue
+        assert cut == 0, words[:3]
+        assert got_opc.tolist() == opc.tolist() and got_pf == pf, words[:3]
+        n_ok += 1
+    assert n_ok >= 90
