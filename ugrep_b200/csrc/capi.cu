@@ -584,20 +584,40 @@ int feed_pageable(ugx_scanner* s, uint8_t* dst, const uint8_t* src, uint64_t n)
       k = 2;
     if (k > 8)
       k = 8;
-    for (unsigned i = 0; i < k; ++i)
+    // all or nothing: a feeder that could not get its streams / pinned slots leaves no half-built state behind
+    cudaError_t e = cudaSuccess;
+    for (unsigned i = 0; i < k && e == cudaSuccess; ++i)
     {
       cudaStream_t st = nullptr;
-      CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+      if (e != cudaSuccess)
+        break;
       s->feed_streams.push_back(st);
-      for (int j = 0; j < 2; ++j)
+      for (int j = 0; j < 2 && e == cudaSuccess; ++j)
       {
         void* p = nullptr;
-        CU(cudaHostAlloc(&p, FEED_CHUNK, cudaHostAllocDefault));
+        e = cudaHostAlloc(&p, FEED_CHUNK, cudaHostAllocDefault);
+        if (e != cudaSuccess)
+          break;
         s->feed_slots.push_back(static_cast<uint8_t*>(p));
         cudaEvent_t ev = nullptr;
-        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        s->feed_events.push_back(ev);
+        e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e == cudaSuccess)
+          s->feed_events.push_back(ev);
       }
+    }
+    if (e != cudaSuccess)
+    {
+      for (uint8_t* p : s->feed_slots)
+        cudaFreeHost(p);
+      for (cudaEvent_t ev : s->feed_events)
+        cudaEventDestroy(ev);
+      for (cudaStream_t st : s->feed_streams)
+        cudaStreamDestroy(st);
+      s->feed_slots.clear();
+      s->feed_events.clear();
+      s->feed_streams.clear();
+      return cuda_fail(e, "pageable feeder setup");
     }
   }
   const unsigned K = static_cast<unsigned>(s->feed_streams.size());
