@@ -272,25 +272,44 @@ def main():
             return sc.find_all_device(pat, data)
         return step
 
-    # ---- corpus: one seeded block, tiled on the device to the named size (line-aligned, so still valid text)
+    # ---- corpus: one seeded block, tiled to the named size.  N = 1: the tiles as they are.  N > 1: ONE logical corpus of
+    # N x reps + 1 tiles, cut into N shards by sharding.tiled_cuts (the nominal cut n*r/N falls inside a line and moves
+    # forward to the next newline), rank r materialises and scans shard r; the path's one exchange — all-gather of the
+    # per-shard {matches, newlines} -> totals and line-number bases — sits inside the timed region of every step.
     block = make_block(cfg)
     reps = max(1, int(gib * GIB) // block.size)
-    nbytes = block.size * reps
     dblock = torch.from_numpy(block).cuda()
-    corpus_dev = dblock.repeat(reps)
     pat = api.Pattern.load(os.path.join(PAT_DIR, CONFIGS[cfg][0] + ".ugxp"), local)
     mode = CONFIGS[cfg][2]
     step = stepper(pat, mode)
-
-    # expected result: the block's count (checked against the oracle below on rank 0) times the number of tiles
-    t1 = step(dblock)
+    t1 = step(dblock)   # the block alone: its count is checked against the oracle below (rank 0)
+    if world > 1:
+        reps_total = world * reps + 1
+        cuts = sharding.tiled_cuts(block, reps_total, world)
+        corpus_dev = sharding.materialize_tiled(dblock, cuts[rank], cuts[rank + 1])
+    else:
+        reps_total = reps
+        cuts = [0, block.size * reps]
+        corpus_dev = dblock.repeat(reps)
     del dblock
-    expect = t1.matches * reps
+    nbytes = int(corpus_dev.numel())               # this rank's shard
+    logical_bytes = block.size * reps_total         # the whole job
+    expect_total = t1.matches * reps_total          # counts are additive over line-aligned pieces
 
+    def exchange(t):
+        if world == 1:
+            return t.matches
+        nl = t.newlines if t.flags & 1 else shard_newlines
+        return sum(c[0] for c in sharding.all_gather_counts(t.matches, nl, device="cuda"))
+
+    # (the streaming `-c` kernels do not count newlines unless asked: the shard's newline count comes from nlcount, once)
+    shard_newlines = sc.count_newlines(corpus_dev).newlines if world > 1 else 0
     for _ in range(args.warmup):
         tot = step(corpus_dev)
-    if tot.matches != expect:
-        raise SystemExit("bench.py: wrong count %d != %d x %d" % (tot.matches, t1.matches, reps))
+        total_matches = exchange(tot)
+    if total_matches != expect_total:
+        raise SystemExit("bench.py: wrong count %d != %d x %d" % (total_matches, t1.matches, reps_total))
+    expect = tot.matches                            # this rank's own count (the e2e legs must reproduce it)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -303,19 +322,16 @@ def main():
     e0.record()
     for _ in range(args.steps):
         tot = step(corpus_dev)
+        total_matches = exchange(tot)
         kernel_ms.append(tot.kernel_ms)
         launches += tot.launches
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    if world > 1:
-        # (the streaming `-c` kernels do not count newlines unless asked: the line-number bases come from nlcount)
-        counts = sharding.all_gather_counts(tot.matches, sc.count_newlines(corpus_dev).newlines, device="cuda")
-        total_matches = sum(c[0] for c in counts)
-    else:
-        total_matches = tot.matches
+    if total_matches != expect_total:
+        raise SystemExit("bench.py: wrong count in the timed region")
     ms_per_step = ms / args.steps
-    value = world * nbytes / (ms_per_step * 1e-3) / 1e9
+    value = logical_bytes / (ms_per_step * 1e-3) / 1e9
 
     # ---- e2e: host buffer through the C ABI, H2D + scan + D2H of the result inside the timed region
     e2e = None
@@ -333,21 +349,19 @@ def main():
             return max_over_ranks(time.perf_counter() - t0)
 
         host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        host.copy_(corpus_dev)          # this rank's shard, byte for byte, in page-locked host memory
         hb = host.numpy()
-        for i in range(reps):
-            hb[i * block.size:(i + 1) * block.size] = block
         esteps = max(3, min(args.steps, 5))
         dt = time_host(hb, esteps)
-        e2e = {"value": round(world * nbytes * esteps / dt / 1e9, 3), "unit": "GB/s",
+        e2e = {"value": round(logical_bytes * esteps / dt / 1e9, 3), "unit": "GB/s",
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 32, "steps": esteps, "host_memory": "pinned"}
-        del host, hb
         # the same from ordinary pageable memory (what an mmap'ing caller hands over without registering it): the
         # library's feeder threads copy it through pinned slots (capi.cu feed_pageable)
         pg = np.empty(nbytes, dtype=np.uint8)
-        for i in range(reps):
-            pg[i * block.size:(i + 1) * block.size] = block
+        pg[:] = hb
+        del host, hb
         dtp = time_host(pg, 2)
-        e2e["pageable"] = {"value": round(world * nbytes * 2 / dtp / 1e9, 3), "unit": "GB/s", "steps": 2}
+        e2e["pageable"] = {"value": round(logical_bytes * 2 / dtp / 1e9, 3), "unit": "GB/s", "steps": 2}
         del pg
 
     if rank == 0:
@@ -494,7 +508,10 @@ def main():
             "config": {"workload": "%s, %.2f GiB per GPU (%d x %d MiB seeded block, line-aligned)"
                                    % (WORKLOAD_TEXT[cfg], nbytes / GIB, reps, block.size >> 20),
                        "config": cfg, "l2": "input (%.1f GiB) larger than L2" % (nbytes / GIB),
-                       "sharding": "one line-aligned shard per GPU, NCCL all-gather of counts only",
+                       "sharding": ("one logical corpus of %d tiles (%.2f GiB) cut into %d line-aligned shards by "
+                                    "sharding.tiled_cuts; NCCL all-gather of {matches, newlines} inside every timed step"
+                                    % (reps_total, logical_bytes / GIB, world)) if world > 1 else "single shard",
+                       "cuts": [int(c) for c in cuts],
                        "dfa_states": info["states"], "byte_classes": info["classes"], "prefilter": info["advance_name"],
                        "table_in_smem": bool(info["table_in_smem"])},
             "hbm_frac": round(value / world / peak, 4),
@@ -507,7 +524,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches,
             "clocks": sampler.summary(),
-            "result": {"count": total_matches, "expected_per_gpu": expect, "oracle": oracle_check},
+            "result": {"count": total_matches, "expected": expect_total, "rank0_count": expect, "oracle": oracle_check},
             "others": others,
         }
         print(json.dumps(line))
