@@ -135,6 +135,8 @@ typedef struct ugx_plan_info {
   uint32_t h4_terms, h4_shift;    /* hashed-predictor terms (steps 3.. of predict_match PMH) */
   uint32_t pm2, pm2_shift;        /* PM4 two-byte term */
   uint32_t lut[256];
+  uint32_t covers;                /* proven by enumeration: every position that starts a non-empty match passes the
+                                     routine's candidate test (so `-c` may skip the test); 0 = not proven or not so */
 } ugx_plan_info;
 
 enum { UGX_MODE_LINES = 0, UGX_MODE_MATCHES = 1, UGX_MODE_RECORDS = 2 }; /* ugrep -c | -c -o | -o -n -b */

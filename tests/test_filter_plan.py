@@ -22,7 +22,7 @@ class PlanInfo(C.Structure):
                                           "advance", "has_meta", "newline_live", "kind", "nterms")] + \
                [("t_off", C.c_uint32 * 3), ("a_off", C.c_uint32 * 2), ("a_chr", C.c_uint32 * 2),
                 ("h4_terms", C.c_uint32), ("h4_shift", C.c_uint32), ("pm2", C.c_uint32), ("pm2_shift", C.c_uint32),
-                ("lut", C.c_uint32 * 256)]
+                ("lut", C.c_uint32 * 256), ("covers", C.c_uint32)]
 
 
 def load_ugxp(path):
@@ -98,6 +98,40 @@ def test_stage1_is_a_superset_of_the_reference_candidates(name):
         total_c += int(cand[:m].sum())
         total_p += int(ok.sum())
     assert total_p >= total_c
+
+
+@pytest.mark.parametrize("name", G.pattern_names())
+def test_covers_flag_agrees_with_the_oracle(name):
+    """`covers` (prefilter_covers_matches: proven by enumeration over the DFA) says that every position starting a
+    non-empty match passes the reference's candidate predicate; check its conclusion against the oracle, position by
+    position, on the golden inputs and corpus blocks (interior positions: the proof leaves the buffer's end out)"""
+    path = G.pattern_path(name)
+    rc, info, pf = describe(path)
+    if rc == 2:
+        pytest.skip("out of scope (rejected at upload)")
+    if not info.covers or info.advance == 0:  # advance_none: every position is attempted, nothing to prove
+        return
+    op = O.OraclePattern(path)
+    inputs = [np.frombuffer(d[:20000], dtype=np.uint8) for _, d in G.cases(name)]
+    inputs += [corpus.block(c, 20000) for c in ("c2", "c4", "c5")]
+    checked = 0
+    for a in inputs:
+        if len(a) < 40:
+            continue
+        cand = op.candidates(a)
+        for p in np.flatnonzero(~cand[:len(a) - 32])[:1500]:
+            cap, ln = op.match_at(a, int(p))
+            assert not (cap and ln), (name, int(p))
+            checked += 1
+    assert checked >= 0
+
+
+def test_covers_is_proven_for_the_word_list_and_refused_for_config3():
+    pat = os.path.join(O.ROOT, "ugrep_b200", "patterns")
+    assert describe(os.path.join(pat, "c2.ugxp"))[1].covers == 1   # PMH over min = 4 bytes of a tree DFA
+    assert describe(os.path.join(pat, "c1.ugxp"))[1].covers == 0   # `one`: the predicate is the match itself
+    assert describe(os.path.join(pat, "c3.ugxp"))[1].covers == 0   # the prefilter has false negatives (SURVEY.md Q1)
+    assert describe(os.path.join(pat, "c5.ugxp"))[1].covers == 0   # look-back: the attempt set is more than cand()
 
 
 def test_dfa_export_shapes_of_the_configs():

@@ -141,6 +141,7 @@ struct ugx_scanner {
   uint64_t* batch = nullptr;      // ugx_count_batch: file table, counters, tile table
   uint64_t batch_cap = 0;
   bool no_span = false;           // counting matches / records take the line-at-a-time kernels (A/B timing, tests)
+  bool no_cover = false;          // the streaming count evaluates the candidate predicate even where it is proven implied
 };
 
 extern "C" {
@@ -220,6 +221,7 @@ static int pattern_create_impl(const uint32_t* opc, uint32_t nop, const ugx_pref
   d.first_leaf = p->dfa.first_leaf;
   d.acc0 = p->dfa.accept[0] != 0;
   ugx::plan_filter(*pf, p->adv, d.plan);
+  d.covers = ugx::prefilter_covers_matches(p->dfa, *pf, p->adv, matcher_flags) ? 1u : 0u;
   d.n_word_ranges = sizeof(k_word_ranges) / sizeof(int) / 2;
   memcpy(d.chr, pf->chr, 256);
   set256(d.cbk, pf->cbk);
@@ -338,6 +340,7 @@ static int plan_describe_impl(const uint32_t* opc, uint32_t nop, const ugx_prefi
   out->newline_live = dfa.newline_live;
   const int adv = ugx::select_advance(*pf, matcher_flags);
   out->advance = adv;
+  out->covers = ugx::prefilter_covers_matches(dfa, *pf, adv, matcher_flags) ? 1u : 0u;
   ugx::FilterPlan plan;
   ugx::plan_filter(*pf, adv, plan);
   out->kind = plan.kind;
@@ -915,6 +918,8 @@ int scan_common(ugx_scanner* s, const ugx_pattern* p, const void* buf, uint64_t 
     sa.totals = s->totals;
     sa.stage_table = 0;
     sa.use_h4 = 0;
+    sa.use_via = 0;
+    sa.no_cover = s->no_cover ? 1u : 0u;
     const uint64_t nreg = ugx::stream_regions(n);
     if (pipelined)
     {
@@ -1172,6 +1177,11 @@ int ugx_scanner_set_option(ugx_scanner* s, const char* name, int value)
   if (strcmp(name, "no_span") == 0)
   {
     s->no_span = value != 0;
+    return UGX_OK;
+  }
+  if (strcmp(name, "no_cover") == 0)
+  {
+    s->no_cover = value != 0;
     return UGX_OK;
   }
   if (strcmp(name, "count_newlines") == 0)

@@ -28,6 +28,7 @@ struct DevPattern {
   uint32_t adv, len, min, pin, lcp, lcs, one, bol, lbk, lbm, flags;
   uint32_t nstates, ncls, has_meta, to_start, nop, n_word_ranges, table_bytes;
   uint32_t first_acc, first_leaf, acc0; // state numbering (pattern_host.hpp); acc0: the start state accepts
+  uint32_t covers;         // proven at upload: every match start passes cand() (pattern_host.hpp prefilter_covers_matches)
   uint32_t pin_a[8], pin_b[8], cbk[8], fst[8]; // 256-bit sets
   uint8_t chr[256];
   const uint8_t* cls;      // [256] byte -> class

@@ -571,6 +571,180 @@ bool prefilter_never_fires(const ugx_prefilter& pf, int adv)
   return false;
 }
 
+// ---- does the prefilter accept every position at which a non-empty match starts? -------------------------------------
+// The candidate predicates of device_pattern.cuh, restated on the host in their interior form (far enough from the end of
+// the buffer that no end-of-buffer clause applies), read a fixed number E of bytes at the position.  Every match start
+// is either an E-byte DFA path that is still alive or a shorter accepted prefix followed by anything; enumerating those
+// strings and evaluating the predicate on each PROVES {p : D(p) > 0} is a subset of the candidates (or finds a
+// counter-example: config 3's false negatives).  The count-lines kernels may then skip the predicate: a line has a match
+// iff some position of it starts one.  Bounded: more than `cap` strings = not proven.
+namespace {
+
+struct CoverCheck {
+  const HostDfa& dfa;
+  const ugx_prefilter& pf;
+  int adv;
+  uint32_t extent;
+  uint64_t budget;
+  const uint8_t* pred;
+  uint32_t pin_a[8] = {0}, pin_b[8] = {0};
+  uint8_t s[320];
+  bool ok = true;
+
+  static uint32_t hash3(uint32_t h, uint32_t b) { return ((h << 3) ^ b) & (UGX_HASH - 1); }
+  static bool in(const uint32_t* set, uint32_t c) { return (set[c >> 5] >> (c & 31)) & 1u; }
+  bool pm4(const uint8_t* p) const
+  {
+    const uint32_t h1 = hash3(p[0], p[1]), h2 = hash3(h1, p[2]), h3 = hash3(h2, p[3]);
+    const uint32_t q = (pred[p[0]] & 0xc0u) | (pred[h1] & 0x30u) | (pred[h2] & 0x0cu) | (pred[h3] & 0x03u);
+    const uint32_t r = ((((((q >> 2) | q) >> 2) | q) >> 1) | q) & 0xffu;
+    return r != 0xffu;
+  }
+  bool pmh(const uint8_t* p, uint32_t n) const
+  {
+    uint32_t h = p[0];
+    uint32_t f = pred[h] & 1u, bit = 2;
+    for (uint32_t j = 1; j < n; ++j, bit <<= 1)
+    {
+      h = hash3(h, p[j]);
+      f |= pred[h] & bit;
+    }
+    return f == 0;
+  }
+  bool tapbit(const uint8_t* p, uint32_t j) const { return (pf.tap[(p[0] ^ (static_cast<uint32_t>(p[1]) << 6)) & (UGX_BTAP - 1)] >> j) & 1u; }
+  bool literal() const { return memcmp(s, pf.chr, pf.len) == 0; }
+
+  bool cand() const
+  {
+    const uint32_t min = pf.min, len = pf.len, lcp = pf.lcp, lcs = pf.lcs;
+    switch (adv)
+    {
+      case UGX_ADV_PIN1_ONE: return s[0] == pf.chr[0] && pm4(s);
+      case UGX_ADV_PIN1_PMA: return s[lcp] == pf.chr[0] && s[lcs] == pf.chr[1] && pm4(s);
+      case UGX_ADV_PIN1_PMH: return s[lcp] == pf.chr[0] && s[lcs] == pf.chr[1] && pmh(s, min);
+      case UGX_ADV_PIN_ONE: return in(pin_a, s[0]) && pm4(s);
+      case UGX_ADV_PIN_PMA: return in(pin_a, s[lcp]) && in(pin_b, s[lcs]) && pm4(s);
+      case UGX_ADV_PIN_PMH: return in(pin_a, s[lcp]) && in(pin_b, s[lcs]) && pmh(s, min);
+      case UGX_ADV_MIN1: return !tapbit(s, 0) && pm4(s);
+      case UGX_ADV_MIN2: return !tapbit(s, 0) && !tapbit(s + 1, 1) && pm4(s);
+      case UGX_ADV_MIN3: return !tapbit(s, 0) && !tapbit(s + 1, 1) && !tapbit(s + 2, 2) && pm4(s);
+      case UGX_ADV_MIN4:
+        for (uint32_t j = 0; j < min; ++j)
+          if (tapbit(s + j, j))
+            return false;
+        return pmh(s, min);
+      case UGX_ADV_PMA: return pm4(s);
+      case UGX_ADV_CHAR: return s[0] == pf.chr[0];
+      case UGX_ADV_CHAR_PMA: return s[0] == pf.chr[0] && pm4(s + 1);
+      case UGX_ADV_CHAR_PMH: return s[0] == pf.chr[0] && pmh(s + 1, min);
+      case UGX_ADV_STRING: return literal();
+      case UGX_ADV_STRING_PMA: return literal() && pm4(s + len);
+      case UGX_ADV_STRING_PMH: return literal() && pmh(s + len, min);
+      case UGX_ADV_NONE: return true;
+      default: return false;
+    }
+  }
+
+  void leaf()
+  {
+    if (budget == 0)
+    {
+      ok = false;
+      return;
+    }
+    --budget;
+    if (!cand())
+      ok = false;
+  }
+
+  // every completion of s[0..depth) to `extent` bytes
+  void pad(uint32_t depth)
+  {
+    if (depth == extent)
+      return leaf();
+    if (extent - depth > 2)
+    {
+      ok = false; // 2^24 completions and more: not enumerated
+      return;
+    }
+    for (uint32_t b = 0; b < 256 && ok; ++b)
+    {
+      s[depth] = static_cast<uint8_t>(b);
+      pad(depth + 1);
+    }
+  }
+
+  void walk(uint32_t state, uint32_t depth)
+  {
+    if (!ok)
+      return;
+    if (depth > 0 && dfa.accept[state] != 0)
+      return pad(depth); // a match ends here: whatever follows, the position starts a match
+    if (depth == extent)
+      return leaf();
+    if (budget == 0)
+    {
+      ok = false;
+      return;
+    }
+    --budget;
+    for (uint32_t b = 0; b < 256 && ok; ++b)
+    {
+      const uint16_t nx = dfa.next[static_cast<size_t>(state) * dfa.ncls + dfa.cls[b]];
+      if (nx == DEAD)
+        continue;
+      s[depth] = static_cast<uint8_t>(b);
+      walk(nx, depth + 1);
+    }
+  }
+};
+
+} // namespace
+
+bool prefilter_covers_matches(const HostDfa& dfa, const ugx_prefilter& pf, int adv, uint32_t matcher_flags, uint32_t cap)
+{
+  if (dfa.has_meta || pf.one || pf.lbk != 0 || (matcher_flags & UGX_OPT_W) != 0)
+    return false; // META edges and option W make D(p) depend on more than the bytes at p; `one`: the predicate IS the match
+  const uint32_t min = pf.min, len = pf.len;
+  uint32_t e;
+  switch (adv)
+  {
+    case UGX_ADV_PIN1_ONE: case UGX_ADV_PIN_ONE: case UGX_ADV_PMA:
+    case UGX_ADV_MIN1: case UGX_ADV_MIN2: case UGX_ADV_MIN3: e = 4; break;
+    case UGX_ADV_PIN1_PMA: case UGX_ADV_PIN_PMA: e = 4; break;
+    case UGX_ADV_PIN1_PMH: case UGX_ADV_PIN_PMH: e = min; break;
+    case UGX_ADV_MIN4: e = min + 1; break;
+    case UGX_ADV_CHAR: e = 1; break;
+    case UGX_ADV_CHAR_PMA: e = 5; break;
+    case UGX_ADV_CHAR_PMH: e = 1 + min; break;
+    case UGX_ADV_STRING: e = len; break;
+    case UGX_ADV_STRING_PMA: e = len + 4; break;
+    case UGX_ADV_STRING_PMH: e = len + min; break;
+    case UGX_ADV_NONE: return true;
+    default: return false;
+  }
+  if (adv == UGX_ADV_PIN1_PMA || adv == UGX_ADV_PIN_PMA || adv == UGX_ADV_PIN1_PMH || adv == UGX_ADV_PIN_PMH)
+  {
+    if (pf.lcp + 1 > e)
+      e = pf.lcp + 1;
+    if (pf.lcs + 1 > e)
+      e = pf.lcs + 1;
+  }
+  if (e == 0 || e > 24) // the kernels guarantee 24 readable bytes after an interior position
+    return false;
+  CoverCheck c{dfa, pf, adv, e, cap, pf.min < 4 ? pf.pma : pf.pmh};
+  if (pf.len == 0 && pf.pin >= 1 && pf.pin <= 16)
+    for (uint32_t i = 0; i < pf.pin; ++i)
+    {
+      const uint32_t a = pf.chr[i], b = pf.chr[pf.pin + i];
+      c.pin_a[a >> 5] |= 1u << (a & 31);
+      c.pin_b[b >> 5] |= 1u << (b & 31);
+    }
+  memset(c.s, 0, sizeof(c.s));
+  c.walk(0, 0);
+  return c.ok;
+}
+
 void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan)
 {
   memset(&plan, 0, sizeof(plan));

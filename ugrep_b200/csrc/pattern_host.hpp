@@ -74,6 +74,11 @@ int flatten_dfa(const uint32_t* opc, uint32_t nop, HostDfa& out, std::string& er
 // (the advance_pattern_min* routines, lib/matcher.cpp:2235-2660, then never stop — config 3)
 bool prefilter_never_fires(const ugx_prefilter& pf, int adv);
 
+// true when it is PROVEN (by enumeration over the DFA, bounded by `cap` strings) that every position at which a non-empty
+// match starts passes the routine's candidate predicate, away from the end of the buffer
+bool prefilter_covers_matches(const HostDfa& dfa, const ugx_prefilter& pf, int adv, uint32_t matcher_flags,
+                              uint32_t cap = 1u << 18);
+
 // first-stage filter of the position-parallel kernels (filter_plan.hpp)
 void plan_filter(const ugx_prefilter& pf, int adv, FilterPlan& plan);
 

@@ -55,6 +55,22 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// read-only table lookups by shared-space address (LDS with a 32-bit address; a generic pointer that may be shared or
+// global compiles to LD.E with 64-bit address arithmetic).  Not volatile: the tables are constant once staged.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
+{
+  uint32_t v;
+  asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
+{
+  uint32_t v;
+  asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+
 __device__ __forceinline__ uint4 lds128(const void* p)
 {
   uint4 v;

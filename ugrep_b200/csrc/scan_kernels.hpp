@@ -66,6 +66,7 @@ struct StreamArgs {
   uint32_t stage_table;           // set by the launcher
   uint32_t use_h4;                // set by the launcher: stage the hashed-predictor term table
   uint32_t use_via;               // set by the launcher: stage the k-gram viability tables (viability.cuh)
+  uint32_t no_cover;              // evaluate the candidate predicate even when DevPattern::covers allows skipping it (A/B)
 };
 
 bool count_lines_stream_eligible(const DevPattern& P);

@@ -22,6 +22,7 @@
 //   * the line that is open at the start of a region cannot be resolved locally: the region publishes
 //     three bits (has newline, success before the first newline, success after the last newline) and
 //     the last CTA to finish chains them over all regions.
+#include <cstdio>
 #include "device_pattern.cuh"
 #include "line_match.cuh"
 #include "scan_kernels.hpp"
@@ -188,6 +189,124 @@ __device__ __noinline__ bool stage2(Text t, const DevPattern& P, Tables T, uint6
   return attempt_at<KIND>(t, P, T, pos);
 }
 
+// the same attempt with the tables staged in shared memory and a start state that does not accept: LDS by 32-bit
+// shared addresses, the pattern's constants in registers, the 8 register bytes unrolled — 7 instructions per transition
+// (the generic form above: 21, with LD.E and the constants re-read from the parameter bank)
+__device__ __forceinline__ bool attempt_staged_first8(const Text& t, const DevPattern& P, uint32_t cls_s, uint32_t next_s,
+                                                      uint32_t ncls, uint32_t first_acc, uint64_t pos, uint32_t lo, uint32_t hi)
+{
+  uint32_t state = 0, nxt = 0;
+  bool done = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+  {
+    if (!done)
+    {
+      const uint32_t ch = __byte_perm(i < 4 ? lo : hi, 0, 0x4440 + (i & 3));
+      nxt = lds_u16(next_s + 2 * (state * ncls + lds_u8(cls_s + ch)));
+      done = nxt >= first_acc;
+      state = nxt;
+    }
+  }
+  if (!done)
+  {
+    // longer than 8 bytes: continue from text memory
+    uint64_t p = pos + 8;
+    for (;;)
+    {
+      if (p >= t.end)
+        return false;
+      const uint32_t ch = t.raw(p++);
+      nxt = lds_u16(next_s + 2 * (state * ncls + lds_u8(cls_s + ch)));
+      if (nxt >= first_acc)
+        break;
+      state = nxt;
+    }
+  }
+  // dead, accepting, or a leaf (accepting unless it is a dead end): the first such state reached decides
+  if (nxt == D_DEAD)
+    return false;
+  if (nxt < P.first_leaf)
+    return true;
+  return (__ldg(P.accept + nxt) & 0x7fffffffu) != 0;
+}
+
+// Stage 2 for a batch of survivors of one span, in rounds of 32 (one survivor per lane).  The first 8 text bytes of an
+// attempt come from three aligned 32-bit loads (they also feed the candidate predicate); `skip_cand`: the survivors need
+// no candidate test (they are exact candidates already, or DevPattern::covers proves that a position starting a match
+// always passes it).  Inlined: the DFA kernels instantiate the span evaluation twice only (full / guarded regions, one
+// span per block), and a call here costs 120 bytes of spills around it (measured: 326 -> 368 GB/s on config 2).
+// (A single flattened loop — a lane that finishes takes its next survivor at once, as in span_scan.cu — was measured
+// SLOWER here, 195 vs 306 GB/s on config 2: a refill is three global loads and the predicate, and every refill of a few
+// lanes stalls the other lanes of the warp.)
+constexpr uint32_t SC_QCAP = 128; // survivor queue entries per warp
+
+#ifndef UGX_DRAIN_ATTR
+#define UGX_DRAIN_ATTR __forceinline__
+#endif
+template <int KIND>
+__device__ UGX_DRAIN_ATTR void drain_queue(Text t, const DevPattern& P, Tables T, uint64_t sbase, const uint16_t* queue,
+                                         uint32_t qn, uint32_t* succ, uint32_t lane, bool skip_cand, bool interior,
+                                         bool staged)
+{
+  if (KIND == SK_META || P.one || !interior)
+  {
+    for (uint32_t base = 0; base < qn; base += 32)
+    {
+      if (base + lane < qn)
+      {
+        const uint32_t off = queue[base + lane];
+        if (stage2<KIND>(t, P, T, sbase + off, skip_cand))
+          atomicOr(&succ[off >> 5], 1u << (off & 31));
+      }
+      __syncwarp();
+    }
+    return;
+  }
+  const uint8_t* __restrict__ sp = t.b + sbase; // 16-byte aligned (a span start)
+  const bool pin_pmh = P.adv == UGX_ADV_PIN_PMH || P.adv == UGX_ADV_PIN1_PMH, pma = P.adv == UGX_ADV_PMA;
+  const uint32_t cls_s = smem_u32(T.cls), next_s = staged ? smem_u32(T.next) : 0u, ncls = P.ncls, first_acc = P.first_acc;
+  staged = staged && P.acc0 == 0;
+  for (uint32_t base = 0; base < qn; base += 32)
+  {
+    if (base + lane < qn)
+    {
+      const uint32_t off = queue[base + lane];
+      const uint32_t sh = (off & 3u) * 8;
+      const uint32_t* a = reinterpret_cast<const uint32_t*>(sp + (off & ~3u));
+      const uint32_t l0 = __ldg(a), l1 = __ldg(a + 1), l2 = __ldg(a + 2);
+      const uint32_t lo = __funnelshift_r(l0, l1, sh), hi = __funnelshift_r(l1, l2, sh);
+      bool ok = true;
+      if (!skip_cand)
+      {
+        if (pin_pmh)
+        {
+          const uint64_t xy = (static_cast<uint64_t>(hi) << 32) | lo;
+          const uint32_t ca = static_cast<uint32_t>(xy >> (8 * P.lcp)) & 0xffu, cb = static_cast<uint32_t>(xy >> (8 * P.lcs)) & 0xffu;
+          if (P.adv == UGX_ADV_PIN1_PMH)
+            ok = ca == P.chr[0] && cb == P.chr[1];
+          else
+            ok = bit256(P.pin_a, ca) && bit256(P.pin_b, cb);
+          ok = ok && pmh_xy(T.pred, lo, hi, P.min);
+        }
+        else if (pma)
+          ok = pm4_x(T.pred, lo);
+        else
+          ok = cand(t, P, T, sbase + off);
+      }
+      if (ok)
+      {
+        const bool hit = staged ? attempt_staged_first8(t, P, cls_s, next_s, ncls, first_acc, sbase + off, lo, hi)
+                                : attempt_table_first8(t, P, T, sbase + off, (static_cast<uint64_t>(hi) << 32) | lo);
+        if (hit)
+          atomicOr(&succ[off >> 5], 1u << (off & 31));
+      }
+    }
+    __syncwarp(); // (also: lanes must have reconverged before this function returns — the caller's own __syncwarp() after
+                  // the call was measured NOT to order a late lane's atomic before an early lane's read of `succ`)
+  }
+}
+
 // exact per-position candidates of one chunk (families without a byte-set plan, spans near the end of the buffer)
 __device__ __noinline__ uint32_t exact_chunk_candidates(Text t, const DevPattern& P, Tables T, uint64_t base, uint32_t w0,
                                                         uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5)
@@ -226,7 +345,7 @@ struct DfaEval {
   const uint32_t* h4x;  // [4096] shared: the same storage when it holds the PM4 pair planes
   uint32_t h4_shift;
   bool pm2;             // lut/h4 hold the PM4 two-byte planes instead (q7 q6 by byte, q5 q4 by pair hash)
-  uint16_t* queue;      // [64] per warp
+  uint16_t* queue;      // [SC_QCAP] per warp
   uint32_t* succ;       // [16] per warp: success bits of the span, bit (16 * lane + k)
   uint32_t nterms, off0, off1, off2;
   bool use_lut;
@@ -235,12 +354,8 @@ struct DfaEval {
   mutable bool via_keep = true;  // ... and the next 63 use it only if that is worth its two lookups per byte
   mutable bool via_first = false; // the table alone picks the survivors (it is at least as selective as the prefilter's
                                   // first-stage planes, which are then not evaluated at all; stage 2 stays exact)
-
-  __device__ __forceinline__ void try_at(uint64_t sbase, uint32_t off, bool exact) const
-  {
-    if (stage2<KIND>(t, P, T, sbase + off, exact))
-      atomicOr(&succ[off >> 5], 1u << (off & 31));
-  }
+  bool cover = false;             // DevPattern::covers: an interior survivor needs no candidate test
+  bool staged = false;            // T.next is the shared-memory copy of the table
 
   __device__ __forceinline__ bool operator()(const uint32_t (&w)[7], uint64_t sbase, uint32_t& succ16) const
   {
@@ -371,11 +486,13 @@ struct DfaEval {
       }
     }
     }
-    // ---- compaction + balanced stage 2.  Per round: a warp scan of the lanes' survivor counts; the lanes whose
-    // survivors fit into the free part of the 64-entry queue write ALL of them (so a lane holding a run of
-    // survivors does not cost one round per survivor); full groups of 32 are then handed out one per lane.
+    // ---- compaction + stage 2.  Per pass: a warp scan of the lanes' survivor counts; the lanes whose survivors fit
+    // into the free part of the queue write ALL of them; the queue is drained (drain_queue) when a lane is left over and
+    // at the end — one pass and one drain for all but the densest spans.
+    const bool skip_cand = exact || (cover && interior);
     uint32_t qn = 0;
-    while (__any_sync(0xffffffffu, surv != 0))
+    bool more;
+    do
     {
       const uint32_t cnt = __popc(surv);
       uint32_t incl = cnt;
@@ -386,8 +503,7 @@ struct DfaEval {
         if (lane >= static_cast<uint32_t>(d))
           incl += y;
       }
-      const uint32_t room = 64u - qn;
-      const bool fits = incl <= room; // monotone over lanes: a prefix of the lanes fits
+      const bool fits = incl <= SC_QCAP - qn; // monotone over lanes: a prefix of the lanes fits
       if (fits)
       {
         uint32_t at = qn + incl - cnt;
@@ -399,21 +515,15 @@ struct DfaEval {
         }
       }
       const uint32_t fitmask = __ballot_sync(0xffffffffu, fits);
-      // entries written = inclusive count of the last fitting lane (at least one lane fits: cnt <= 16 <= room
-      // whenever qn < 32, which the flush below guarantees)
-      const uint32_t last_fit = 31u - __clz(fitmask);
-      qn += __shfl_sync(0xffffffffu, incl, last_fit);
+      // entries written = inclusive count of the last fitting lane (an empty queue takes at least lane 0: cnt <= 16)
+      if (fitmask != 0)
+        qn += __shfl_sync(0xffffffffu, incl, 31u - __clz(fitmask));
+      more = fitmask != 0xffffffffu;
       __syncwarp();
-      while (qn >= 32)
-      {
-        qn -= 32;
-        try_at(sbase, queue[qn + lane], exact);
-        __syncwarp();
-      }
-    }
-    if (lane < qn)
-      try_at(sbase, queue[lane], exact);
-    __syncwarp();
+      drain_queue<KIND>(t, P, T, sbase, queue, qn, succ, lane, skip_cand, interior, staged);
+      qn = 0;
+      __syncwarp();
+    } while (more);
     const uint32_t word = succ[lane >> 1];
     __syncwarp();
     if (lane < 16)
@@ -441,7 +551,7 @@ count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* _
   uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_tap + UGX_BTAP);
   uint32_t* s_succ = s_lut + 256;
   uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_succ + 16 * NWARPS);
-  uint32_t* s_h4 = reinterpret_cast<uint32_t*>(s_queue + 64 * NWARPS);
+  uint32_t* s_h4 = reinterpret_cast<uint32_t*>(s_queue + SC_QCAP * NWARPS);
   uint8_t* s_via = reinterpret_cast<uint8_t*>(s_h4 + (a.use_h4 ? UGX_HASH : 0));
   uint16_t* s_next = reinterpret_cast<uint16_t*>(s_via + (a.use_via ? via_smem_bytes(P) : 0));
   // ---- tables -> shared memory by bulk asynchronous copies (cp.async.bulk, the TMA path without a tensor map)
@@ -475,9 +585,11 @@ count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* _
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   DfaEval<KIND> ev{P, T, Text{buf, n}, lane, (lane + 1) & 31, s_lut, a.use_h4 ? s_h4 : nullptr, s_h4, P.plan.h4_shift,
                    P.plan.pm2 != 0 && a.use_h4 != 0,
-                   s_queue + 64 * wid, s_succ + 16 * wid,
+                   s_queue + SC_QCAP * wid, s_succ + 16 * wid,
                    P.plan.nterms, P.plan.t_off[0], P.plan.t_off[1], P.plan.t_off[2],
                    P.plan.kind == FK_LUT && P.plan.nterms >= 1, via};
+  ev.cover = P.covers != 0 && a.no_cover == 0 && KIND == SK_TABLE;
+  ev.staged = a.stage_table != 0;
   stream_scan<WANT_NL, false, 1>(buf, n, a, ev);
 }
 
@@ -487,7 +599,7 @@ static bool stream_use_via(const DevPattern& P) { return P.via_k != 0 && P.has_m
 
 static size_t stream_smem_bytes(const DevPattern& P, bool stage, int threads)
 {
-  return 256 + UGX_HASH + UGX_BTAP + 1024 + (threads / 32) * (64 + 128) + (stream_use_h4(P) ? 4 * UGX_HASH : 0) +
+  return 256 + UGX_HASH + UGX_BTAP + 1024 + (threads / 32) * (64 + 2 * SC_QCAP) + (stream_use_h4(P) ? 4 * UGX_HASH : 0) +
          (stream_use_via(P) ? via_smem_bytes(P) : 0) + (stage ? ((P.table_bytes + 15) / 16) * 16 : 0);
 }
 
