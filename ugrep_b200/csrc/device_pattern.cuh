@@ -14,6 +14,7 @@
 
 #include "../../include/ugrep_b200.h"
 #include "filter_plan.hpp"
+#include "ptx.cuh"
 
 namespace ugx {
 
@@ -52,6 +53,26 @@ struct Tables {
   const uint16_t* next;
   const uint8_t* pred;
   const uint8_t* tap;
+};
+
+// one DFA transition with the lookups by shared-space address (LDS with a 32-bit address and the pattern's constants in
+// registers; through the generic pointers of Tables the same transition compiles to LD.E with 64-bit address arithmetic
+// and re-reads of the parameter bank — three times the instructions).  The class map is always staged; the table is
+// read from global memory when it does not fit (next_s == 0).
+struct Stepper {
+  uint32_t cls_s, next_s, ncls;
+  const uint16_t* gnext;
+  __device__ __forceinline__ Stepper(const Tables& T, uint32_t ncls_, bool staged)
+      : cls_s(smem_u32(T.cls)), next_s(staged ? smem_u32(T.next) : 0u), ncls(ncls_), gnext(T.next)
+  {
+    // opaque to the compiler, which otherwise rebuilds the shared-window addresses from special registers per use
+    asm volatile("" : "+r"(cls_s), "+r"(next_s), "+r"(ncls));
+  }
+  __device__ __forceinline__ uint32_t operator()(uint32_t state, uint32_t ch) const
+  {
+    const uint32_t idx = state * ncls + lds_u8(cls_s + ch);
+    return next_s != 0 ? lds_u16(next_s + 2 * idx) : static_cast<uint32_t>(__ldg(gnext + idx));
+  }
 };
 
 __device__ __forceinline__ bool bit256(const uint32_t* set, uint32_t c) { return (set[c >> 5] >> (c & 31)) & 1u; }

@@ -248,6 +248,7 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
   uint32_t* dtab = s_dtab + wid * SP_SPAN;
   uint32_t* succ = s_succ + wid * 16;
   uint16_t* queue = s_queue + wid * SP_SPAN;
+  const Stepper step(T, P.ncls, a.stage_table != 0);
   const bool has_lb = P.lbk != 0;
   // lazy attempt set: the prefilter's masks cost table lookups per byte (PM4 at every byte, bitap), and the viability
   // table is there to name the few positions worth asking about — membership in A is then decided per viable position
@@ -361,7 +362,7 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
         __syncwarp();
         const uint8_t* __restrict__ sp = buf + sbase;
         const uint32_t rel_end = n - sbase > 0x7fffffffull ? 0x7fffffffu : static_cast<uint32_t>(n - sbase);
-        const uint32_t first_acc = P.first_acc, ncls = P.ncls;
+        const uint32_t first_acc = P.first_acc;
         uint32_t i = lane, off = 0, pp = 0, state = 0, best = 0;
         bool active = false;
         for (;;)
@@ -393,7 +394,7 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
           {
             const uint32_t ch = __ldg(sp + pp);
             ++pp;
-            const uint32_t nx = T.next[state * ncls + T.cls[ch]];
+            const uint32_t nx = step(state, ch);
             if (nx == D_DEAD)
               stop = true;
             else
@@ -580,7 +581,7 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
 }
 
 // one anchored attempt for a known match start: (accept << 16) | length of the longest match
-__device__ __forceinline__ uint32_t longest_at(const Text& t, const DevPattern& P, const Tables& T, uint64_t pos)
+__device__ __forceinline__ uint32_t longest_at(const Text& t, const DevPattern& P, const Stepper& step, uint64_t pos)
 {
   if (P.one)
     return (1u << 16) | P.len;
@@ -590,7 +591,7 @@ __device__ __forceinline__ uint32_t longest_at(const Text& t, const DevPattern& 
   {
     if (p >= t.end)
       break;
-    const uint32_t nx = T.next[state * P.ncls + T.cls[t.raw(p++)]];
+    const uint32_t nx = step(state, t.raw(p++));
     if (nx == D_DEAD)
       break;
     if (nx >= P.first_acc)
@@ -629,6 +630,7 @@ span_emit_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
   T.pred = s_pred;
   T.tap = s_tap;
   T.next = a.stage_table ? s_next : P.next;
+  const Stepper step(T, P.ncls, a.stage_table != 0);
   const Text t{buf, n};
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint64_t limit = __ldcg(a.tail);
@@ -672,7 +674,7 @@ span_emit_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
       {
         const uint32_t k = __ffs(sel) - 1;
         sel &= sel - 1;
-        const uint32_t d = longest_at(t, P, T, base + k);
+        const uint32_t d = longest_at(t, P, step, base + k);
         ugx_match rec;
         rec.line = lno + __popc(nl & ((1u << k) - 1u));
         rec.offset = base + k + a.base_offset;
