@@ -87,8 +87,13 @@ def main():
         tot[3] += wf
     print("kernel:", kname[:120])
     print("total warp-inst %d, thread-inst %d, samples %d, smem wavefronts %d, SASS insts %d" % (*tot, n_inst))
+    per_file = {}
+    for (f, l), a in agg.items():
+        per_file[f] = per_file.get(f, 0) + a[0]
+    print("per file: " + ", ".join("%s %.1f%%" % (f, 100.0 * v / max(1, tot[0])) for f, v in sorted(per_file.items(), key=lambda kv: -kv[1])))
     srcs = {}
-    for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+    top = int(os.environ.get("NCU_HOT_TOP", "40"))
+    for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
         if f not in srcs:
             p = os.path.join(ROOT, "ugrep_b200", "csrc", f)
             srcs[f] = open(p).read().splitlines() if os.path.exists(p) else []

@@ -259,6 +259,16 @@ static int pattern_create_impl(const uint32_t* opc, uint32_t nop, const ugx_pref
     via_t[2 * b] = via.t01[b];
     via_t[2 * b + 1] = via.t23[b];
   }
+  if (via.k != 0 && via.bits.size() * 32 <= 8192)
+  {
+    // a small table is stored one byte per entry: the device then needs one load per position instead of load, shift, mask
+    std::vector<uint32_t> bytes(via.bits.size() * 8, 0);
+    for (size_t i = 0; i < via.bits.size() * 32; ++i)
+      if ((via.bits[i >> 5] >> (i & 31)) & 1u)
+        bytes[i >> 2] |= 1u << (8 * (i & 3));
+    via.bits.swap(bytes);
+    d.via_bytes = 1;
+  }
   via.bits.resize((via.bits.size() + 3) / 4 * 4 + 4, 0); // whole uint4s for the staging copy
   via.pair.resize((via.pair.size() + 15) / 16 * 16 + 16, 0);
   d.via_words = static_cast<uint32_t>(via.bits.size());
@@ -754,6 +764,7 @@ int scan_spans(ugx_scanner* s, const ugx_pattern* p, const uint8_t* dbuf, uint64
   a.sel_bits = want_records ? s->span_sel : nullptr;
   a.base_offset = base_offset;
   a.base_line = base_line;
+  a.no_cover = s->no_cover ? 1u : 0u;
   a.tail = reinterpret_cast<const uint64_t*>(s->totals + 5);
   a.flags = reinterpret_cast<unsigned int*>(s->totals + 6);
   CU(cudaMemsetAsync(s->totals + 6, 0, sizeof(unsigned long long), s->stream));

@@ -42,6 +42,7 @@ struct DevPattern {
   FilterPlan plan;         // first-stage filter of the position-parallel kernels
   // k-gram viability of an anchored attempt (pattern_host.hpp Viability; span_scan.cu)
   uint32_t via_k, via_stride, via_words, via_pair_bytes;
+  uint32_t via_bytes;        // via_bits holds one BYTE per entry (small tables: one lookup, no shift / mask per position)
   const uint32_t* via_ids;   // [512] t01 / t23 interleaved: one 64-bit lookup per text byte
   const uint32_t* via_bits;  // [via_words] (a multiple of 4 words)
   const uint8_t* via_pair;   // [via_pair_bytes] (a multiple of 16 bytes)

@@ -703,8 +703,9 @@ struct CoverCheck {
 
 bool prefilter_covers_matches(const HostDfa& dfa, const ugx_prefilter& pf, int adv, uint32_t matcher_flags, uint32_t cap)
 {
-  if (dfa.has_meta || pf.one || pf.lbk != 0 || (matcher_flags & UGX_OPT_W) != 0)
+  if (dfa.has_meta || pf.one || (matcher_flags & UGX_OPT_W) != 0)
     return false; // META edges and option W make D(p) depend on more than the bytes at p; `one`: the predicate IS the match
+  // (look-back only ADDS positions to the attempt set, A = cand | (cbk & A + 1): cand covering the match starts is enough)
   const uint32_t min = pf.min, len = pf.len;
   uint32_t e;
   switch (adv)

@@ -108,6 +108,7 @@ struct SpanArgs {
   unsigned int* flags;     // device: bit 0 an attempt failed at the end of the buffer, bit 1 a match too long for the span tables
   uint32_t stage_table;    // set by the launcher
   uint32_t use_via;        // set by the launcher: the viability tables are staged in shared memory
+  uint32_t no_cover;       // decide membership in the attempt set even when DevPattern::covers makes it moot (A/B)
 };
 
 bool span_scan_eligible(const DevPattern& P);

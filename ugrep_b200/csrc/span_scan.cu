@@ -255,6 +255,7 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
   const bool lazy = via.on && (P.adv == UGX_ADV_PMA || P.adv == UGX_ADV_MIN1 || P.adv == UGX_ADV_MIN2 ||
                                P.adv == UGX_ADV_MIN3 || P.adv == UGX_ADV_MIN4);
   const bool mask_lb = has_lb && !lazy;
+  const bool cover = P.covers != 0 && a.no_cover == 0;
   const uint64_t limit = __ldcg(a.tail); // spans own [0, limit): the last line belongs to the final kernel
   const uint64_t nregions = (limit + SC_REGION - 1) / SC_REGION;
   const uint64_t total_warps = static_cast<uint64_t>(gridDim.x) * NWARPS;
@@ -373,7 +374,9 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
               break;
             off = queue[i];
             i += 32;
-            if (lazy && !in_attempt_set(t, P, T, s_flags, sbase + off, bad))
+            // (a position that starts a match is in A when `cover` holds — away from the end of the buffer, where the
+            // prefilters' clauses differ — and one that does not start a match does not count either way)
+            if (lazy && (!cover || sbase + off + 32 > t.end) && !in_attempt_set(t, P, T, s_flags, sbase + off, bad))
               continue;
             if (P.one)
             {

@@ -14,6 +14,7 @@ struct ViaTables {
   const uint32_t* bits; // shared
   uint32_t stride;
   bool on;
+  bool bytes;           // `bits` holds one byte per entry
 };
 
 __host__ __device__ inline uint32_t via_smem_bytes(const DevPattern& P) { return P.via_k ? 2048 + P.via_pair_bytes + P.via_words * 4 : 0; }
@@ -24,6 +25,7 @@ __device__ __forceinline__ ViaTables via_stage(const DevPattern& P, uint8_t* bas
   ViaTables v;
   v.on = on && P.via_k != 0;
   v.stride = P.via_stride;
+  v.bytes = P.via_bytes != 0;
   uint32_t* t = reinterpret_cast<uint32_t*>(base);
   uint32_t* bits = t + 512;
   uint8_t* pair = reinterpret_cast<uint8_t*>(bits + P.via_words);
@@ -47,6 +49,21 @@ __device__ __forceinline__ uint32_t viable16(const ViaTables& v, const Window& W
 {
   uint2 a = v.t[UGX_WB(W, 0)], b = v.t[UGX_WB(W, 1)], c = v.t[UGX_WB(W, 2)];
   uint32_t m = 0;
+  if (v.bytes)
+  {
+    const uint8_t* flag = reinterpret_cast<const uint8_t*>(v.bits);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+    {
+      const uint2 d = v.t[UGX_WB(W, k + 3)];
+      const uint32_t code = v.pair[(a.x & 0xffffu) + (b.x >> 16)];
+      m += static_cast<uint32_t>(flag[code * v.stride + (c.y & 0xffffu) + (d.y >> 16)]) << k;
+      a = b;
+      b = c;
+      c = d;
+    }
+    return m;
+  }
 #pragma unroll
   for (int k = 0; k < 16; ++k)
   {
