@@ -171,6 +171,65 @@ __device__ __forceinline__ bool in_attempt_set(const Text& t, const DevPattern& 
   }
 }
 
+// the longest anchored match at offset `off` of the span at `sp` (16-byte aligned): (accept << 16) | length, 0 = none.
+// The first 8 bytes come from three aligned 32-bit loads and are stepped through unrolled; `bad`: bit 1 a match too long
+// for the table, bit 0 the attempt failed after reading up to the end of the buffer (see the file header)
+__device__ __forceinline__ uint32_t longest_in_span(const DevPattern& P, const Stepper& step, const uint8_t* __restrict__ sp,
+                                                    uint32_t off, uint32_t rel_end, uint32_t& bad)
+{
+  const uint32_t first_acc = P.first_acc;
+  uint32_t state = 0, best = 0, pp = off;
+  bool stop = false;
+  // nx >= first_acc: dead, accepting, or without outgoing edges (the interpreter halts there before reading)
+  auto special = [&](uint32_t nx) {
+    if (nx == D_DEAD)
+    {
+      stop = true;
+      return;
+    }
+    const uint32_t acc = __ldg(P.accept + nx);
+    if ((acc & 0x7fffffffu) != 0)
+    {
+      const uint32_t len = pp - off;
+      if (len >= SP_LONG || (acc & 0x7fffffffu) >= 0x8000u)
+        bad |= 2u;
+      best = ((acc & 0x7fffu) << 16) | (len & 0xffffu);
+    }
+    if ((acc & 0x80000000u) != 0)
+      stop = true;
+  };
+  if (off + 12 <= rel_end)
+  {
+    const uint32_t sh = (off & 3u) * 8;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(sp + (off & ~3u));
+    const uint32_t l0 = __ldg(a), l1 = __ldg(a + 1), l2 = __ldg(a + 2);
+    const uint32_t lo = __funnelshift_r(l0, l1, sh), hi = __funnelshift_r(l1, l2, sh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+    {
+      if (!stop)
+      {
+        const uint32_t nx = step(state, __byte_perm(i < 4 ? lo : hi, 0, 0x4440 + (i & 3)));
+        ++pp;
+        if (nx >= first_acc)
+          special(nx);
+        state = nx;
+      }
+    }
+  }
+  while (!stop && pp < rel_end)
+  {
+    const uint32_t nx = step(state, __ldg(sp + pp));
+    ++pp;
+    if (nx >= first_acc)
+      special(nx);
+    state = nx;
+  }
+  if (best == 0 && pp >= rel_end)
+    bad |= 1u;
+  return best;
+}
+
 } // namespace
 
 // the start of the buffer's last line, if that line is at most SPAN_TAIL_MAX bytes long: tail[0] = its offset, else n
@@ -338,9 +397,7 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
         }
         a16 &= cur.via; // a position that cannot start a match needs no attempt (its D is 0 either way)
       }
-      // ---- 3. D(p) for the positions of A: compaction, then ONE loop whose body is a single DFA transition — a lane
-      // that finishes an attempt takes its next position in the same iteration, so the lanes keep stepping together
-      // whatever the lengths of their attempts
+      // ---- 3. D(p) for the positions of A: compaction, then rounds of one position per lane (longest_in_span)
       {
         const uint32_t cnt = __popc(a16);
         uint32_t incl = cnt;
@@ -363,71 +420,34 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
         __syncwarp();
         const uint8_t* __restrict__ sp = buf + sbase;
         const uint32_t rel_end = n - sbase > 0x7fffffffull ? 0x7fffffffu : static_cast<uint32_t>(n - sbase);
-        const uint32_t first_acc = P.first_acc;
-        uint32_t i = lane, off = 0, pp = 0, state = 0, best = 0;
-        bool active = false;
-        for (;;)
+        // rounds of 32 positions, one per lane (the viability table leaves less than a round per span on config 5)
+        for (uint32_t qb = 0; qb < total; qb += 32)
         {
-          if (!active)
+          if (qb + lane < total)
           {
-            if (i >= total)
-              break;
-            off = queue[i];
-            i += 32;
+            const uint32_t off = queue[qb + lane];
             // (a position that starts a match is in A when `cover` holds — away from the end of the buffer, where the
             // prefilters' clauses differ — and one that does not start a match does not count either way)
-            if (lazy && (!cover || sbase + off + 32 > t.end) && !in_attempt_set(t, P, T, s_flags, sbase + off, bad))
-              continue;
-            if (P.one)
+            if (!lazy || (cover && sbase + off + 32 <= t.end) || in_attempt_set(t, P, T, s_flags, sbase + off, bad))
             {
-              // the candidate test was the exact literal (lib/matcher.cpp:71-83)
-              if (P.len >= SP_LONG)
-                bad |= 2u;
-              dtab[off] = (1u << 16) | P.len;
-              atomicOr(&succ[off >> 5], 1u << (off & 31));
-              continue;
-            }
-            pp = off;
-            state = 0;
-            best = 0;
-            active = true;
-          }
-          bool stop = pp >= rel_end;
-          if (!stop)
-          {
-            const uint32_t ch = __ldg(sp + pp);
-            ++pp;
-            const uint32_t nx = step(state, ch);
-            if (nx == D_DEAD)
-              stop = true;
-            else
-            {
-              if (nx >= first_acc)
+              uint32_t best;
+              if (P.one)
               {
-                const uint32_t acc = __ldg(P.accept + nx);
-                if ((acc & 0x7fffffffu) != 0)
-                {
-                  const uint32_t len = pp - off;
-                  if (len >= SP_LONG || (acc & 0x7fffffffu) >= 0x8000u)
-                    bad |= 2u;
-                  best = ((acc & 0x7fffu) << 16) | (len & 0xffffu);
-                }
-                stop = (acc & 0x80000000u) != 0; // no outgoing edges: the interpreter halts here before reading
+                // the candidate test was the exact literal (lib/matcher.cpp:71-83)
+                if (P.len >= SP_LONG)
+                  bad |= 2u;
+                best = (1u << 16) | P.len;
               }
-              state = nx;
+              else
+                best = longest_in_span(P, step, sp, off, rel_end, bad);
+              if (best != 0)
+              {
+                dtab[off] = best;
+                atomicOr(&succ[off >> 5], 1u << (off & 31));
+              }
             }
           }
-          if (stop)
-          {
-            if (best != 0)
-            {
-              dtab[off] = best;
-              atomicOr(&succ[off >> 5], 1u << (off & 31));
-            }
-            else if (pp >= rel_end)
-              bad |= 1u; // failed after reading up to the end of the buffer (see the file header)
-            active = false;
-          }
+          __syncwarp();
         }
         __syncwarp();
       }

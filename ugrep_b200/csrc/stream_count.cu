@@ -540,7 +540,7 @@ template <int KIND, bool WANT_NL, int THREADS>
 #ifndef UGX_DFA_MINB
 #define UGX_DFA_MINB 3
 #endif
-__global__ void __launch_bounds__(THREADS, THREADS >= 1024 ? 1 : UGX_DFA_MINB)
+__global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 1 : UGX_DFA_MINB)
 count_lines_stream_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict__ buf, uint64_t n, StreamArgs a)
 {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -626,6 +626,10 @@ int stream_grid(uint64_t n, int sm_count, int per_sm, int threads)
   return static_cast<int>(g);
 }
 
+#ifndef UGX_BIG_THREADS
+#define UGX_BIG_THREADS 1024 // a big staged table leaves room for one CTA per SM
+#endif
+
 template <int KIND, bool WANT_NL, int THREADS>
 static cudaError_t launch_dfa(const DevPattern& P, const uint8_t* buf, uint64_t n, const StreamArgs& a, size_t smem,
                               int sm_count, cudaStream_t st)
@@ -651,7 +655,7 @@ cudaError_t launch_count_lines_stream(const DevPattern& P, const uint8_t* buf, u
   const bool stage = !meta && stream_smem_bytes(P, true, 1024) <= static_cast<size_t>(UGX_MAX_DYN_SMEM);
   // a big staged table leaves room for one CTA per SM: make it a full 1024-thread CTA
   const bool big = stage && stream_smem_bytes(P, true, 256) > 100 * 1024;
-  const size_t smem = stream_smem_bytes(P, stage, big ? 1024 : 256);
+  const size_t smem = stream_smem_bytes(P, stage, big ? UGX_BIG_THREADS : 256);
   a.stage_table = stage ? 1u : 0u;
   a.use_h4 = stream_use_h4(P) ? 1u : 0u;
   a.use_via = stream_use_via(P) ? 1u : 0u;
@@ -659,8 +663,8 @@ cudaError_t launch_count_lines_stream(const DevPattern& P, const uint8_t* buf, u
     return want_nl ? launch_dfa<SK_META, true, 256>(P, buf, n, a, smem, sm_count, st)
                    : launch_dfa<SK_META, false, 256>(P, buf, n, a, smem, sm_count, st);
   if (big)
-    return want_nl ? launch_dfa<SK_TABLE, true, 1024>(P, buf, n, a, smem, sm_count, st)
-                   : launch_dfa<SK_TABLE, false, 1024>(P, buf, n, a, smem, sm_count, st);
+    return want_nl ? launch_dfa<SK_TABLE, true, UGX_BIG_THREADS>(P, buf, n, a, smem, sm_count, st)
+                   : launch_dfa<SK_TABLE, false, UGX_BIG_THREADS>(P, buf, n, a, smem, sm_count, st);
   return want_nl ? launch_dfa<SK_TABLE, true, 256>(P, buf, n, a, smem, sm_count, st)
                  : launch_dfa<SK_TABLE, false, 256>(P, buf, n, a, smem, sm_count, st);
 }
