@@ -74,6 +74,13 @@ struct Stepper {
     const uint32_t idx = state * ncls + lds_u8(cls_s + ch);
     return next_s != 0 ? lds_u16(next_s + 2 * idx) : static_cast<uint32_t>(__ldg(gnext + idx));
   }
+  // the same with the table's place known at compile time (no branch per transition)
+  template <bool STAGED>
+  __device__ __forceinline__ uint32_t at(uint32_t state, uint32_t ch) const
+  {
+    const uint32_t idx = state * ncls + lds_u8(cls_s + ch);
+    return STAGED ? lds_u16(next_s + 2 * idx) : static_cast<uint32_t>(__ldg(gnext + idx));
+  }
 };
 
 __device__ __forceinline__ bool bit256(const uint32_t* set, uint32_t c) { return (set[c >> 5] >> (c & 31)) & 1u; }

@@ -189,11 +189,13 @@ __device__ __noinline__ bool stage2(Text t, const DevPattern& P, Tables T, uint6
   return attempt_at<KIND>(t, P, T, pos);
 }
 
-// the same attempt with the tables staged in shared memory and a start state that does not accept: LDS by 32-bit
-// shared addresses, the pattern's constants in registers, the 8 register bytes unrolled — 7 instructions per transition
-// (the generic form above: 21, with LD.E and the constants re-read from the parameter bank)
-__device__ __forceinline__ bool attempt_staged_first8(const Text& t, const DevPattern& P, uint32_t cls_s, uint32_t next_s,
-                                                      uint32_t ncls, uint32_t first_acc, uint64_t pos, uint32_t lo, uint32_t hi)
+// the same attempt for a start state that does not accept, transitions through a Stepper (device_pattern.cuh): LDS by
+// 32-bit shared addresses when the table is staged, the pattern's constants in registers, the 8 register bytes unrolled
+// and predicated — 9 instructions per transition (the generic form above: 21, with LD.E and the constants re-read from
+// the parameter bank)
+template <bool STAGED>
+__device__ __forceinline__ bool attempt_step_first8(const Text& t, const DevPattern& P, const Stepper& step, uint32_t first_acc,
+                                                    uint64_t pos, uint32_t lo, uint32_t hi)
 {
   uint32_t state = 0, nxt = 0;
   bool done = false;
@@ -202,8 +204,7 @@ __device__ __forceinline__ bool attempt_staged_first8(const Text& t, const DevPa
   {
     if (!done)
     {
-      const uint32_t ch = __byte_perm(i < 4 ? lo : hi, 0, 0x4440 + (i & 3));
-      nxt = lds_u16(next_s + 2 * (state * ncls + lds_u8(cls_s + ch)));
+      nxt = step.template at<STAGED>(state, __byte_perm(i < 4 ? lo : hi, 0, 0x4440 + (i & 3)));
       done = nxt >= first_acc;
       state = nxt;
     }
@@ -216,8 +217,7 @@ __device__ __forceinline__ bool attempt_staged_first8(const Text& t, const DevPa
     {
       if (p >= t.end)
         return false;
-      const uint32_t ch = t.raw(p++);
-      nxt = lds_u16(next_s + 2 * (state * ncls + lds_u8(cls_s + ch)));
+      nxt = step.template at<STAGED>(state, t.raw(p++));
       if (nxt >= first_acc)
         break;
       state = nxt;
@@ -265,8 +265,9 @@ __device__ UGX_DRAIN_ATTR void drain_queue(Text t, const DevPattern& P, Tables T
   }
   const uint8_t* __restrict__ sp = t.b + sbase; // 16-byte aligned (a span start)
   const bool pin_pmh = P.adv == UGX_ADV_PIN_PMH || P.adv == UGX_ADV_PIN1_PMH, pma = P.adv == UGX_ADV_PMA;
-  const uint32_t cls_s = smem_u32(T.cls), next_s = staged ? smem_u32(T.next) : 0u, ncls = P.ncls, first_acc = P.first_acc;
-  staged = staged && P.acc0 == 0;
+  const Stepper step(T, P.ncls, staged);
+  const uint32_t first_acc = P.first_acc;
+  const bool acc0 = P.acc0 != 0;
   for (uint32_t base = 0; base < qn; base += 32)
   {
     if (base + lane < qn)
@@ -296,8 +297,9 @@ __device__ UGX_DRAIN_ATTR void drain_queue(Text t, const DevPattern& P, Tables T
       }
       if (ok)
       {
-        const bool hit = staged ? attempt_staged_first8(t, P, cls_s, next_s, ncls, first_acc, sbase + off, lo, hi)
-                                : attempt_table_first8(t, P, T, sbase + off, (static_cast<uint64_t>(hi) << 32) | lo);
+        const bool hit = acc0      ? attempt_table_first8(t, P, T, sbase + off, (static_cast<uint64_t>(hi) << 32) | lo)
+                         : staged ? attempt_step_first8<true>(t, P, step, first_acc, sbase + off, lo, hi)
+                                  : attempt_step_first8<false>(t, P, step, first_acc, sbase + off, lo, hi);
         if (hit)
           atomicOr(&succ[off >> 5], 1u << (off & 31));
       }
