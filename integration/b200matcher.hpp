@@ -27,6 +27,7 @@
 
 #include <reflex/matcher.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -200,6 +201,8 @@ class B200Matcher : public reflex::Matcher {
   void scan_input()
   {
     fresh_ = false;
+    const bool verbose = env_set("UGREP_B200_VERBOSE");
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     // Read the rest of the input in full, the way peek_more() does block by block (absmatcher.h:1612-1631): grow()
     // shifts out what lies before the current line (calling the caller's handler, keeping lno_ / num_ right) or
     // enlarges the buffer.  (AbstractMatcher::buffer() is not used: it assumes nothing has been read yet, and
@@ -224,9 +227,19 @@ class B200Matcher : public reflex::Matcher {
     lpb_line_ = lno_;
     const ugx_match *dev = NULL;
     uint64_t n = 0;
-    const int rc = ugx_find_all_device(scanner_, shared_->pattern, buf_, end_, 0, base_line, &dev, &n, NULL);
+    ugx_totals tot;
+    memset(&tot, 0, sizeof(tot));
+    const std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
+    const int rc = ugx_find_all_device(scanner_, shared_->pattern, buf_, end_, 0, base_line, &dev, &n, &tot);
     if (rc != UGX_OK)
       throw std::runtime_error(std::string("ugrep-b200: ") + ugx_last_error());
+    if (verbose)
+    {
+      const std::chrono::steady_clock::time_point t2 = std::chrono::steady_clock::now();
+      fprintf(stderr, "ugrep-b200: %zu bytes in memory after %.3f s; device scan %.3f s (kernels %.3f ms, %u launches), %llu records\n",
+              static_cast<size_t>(end_), std::chrono::duration<double>(t1 - t0).count(),
+              std::chrono::duration<double>(t2 - t1).count(), tot.kernel_ms, tot.launches, static_cast<unsigned long long>(n));
+    }
     count_ = n;
     next_ = 0;
     batch_first_ = 0;

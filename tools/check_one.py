@@ -15,7 +15,8 @@ from ugrep_b200 import api, corpus  # noqa: E402
 import oracle_lib as O  # noqa: E402
 
 CFG = {"c1": ("c1", "c1", "lines"), "c2": ("c2", "c2", "lines"), "c2s": ("c2", "c2s", "lines"), "c3b": ("c3b", "c3", "list"),
-       "c4": ("c4", "c4", "lines"), "c5": ("c5", "c5", "matches"), "c5l": ("c5", "c5", "lines"), "c3bm": ("c3b", "c3", "matches")}
+       "c4": ("c4", "c4", "lines"), "c5": ("c5", "c5", "matches"), "c5l": ("c5", "c5", "lines"), "c3bm": ("c3b", "c3", "matches"),
+       "c2m": ("c2", "c2", "matches"), "c2r": ("c2", "c2", "list"), "c2sm": ("c2", "c2s", "matches")}
 
 
 def main():

@@ -311,10 +311,12 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
   const bool has_lb = P.lbk != 0;
   // lazy attempt set: the prefilter's masks cost table lookups per byte (PM4 at every byte, bitap), and the viability
   // table is there to name the few positions worth asking about — membership in A is then decided per viable position
-  const bool lazy = via.on && (P.adv == UGX_ADV_PMA || P.adv == UGX_ADV_MIN1 || P.adv == UGX_ADV_MIN2 ||
-                               P.adv == UGX_ADV_MIN3 || P.adv == UGX_ADV_MIN4);
-  const bool mask_lb = has_lb && !lazy;
+  const bool lazy_fam = via.on && (P.adv == UGX_ADV_PMA || P.adv == UGX_ADV_MIN1 || P.adv == UGX_ADV_MIN2 ||
+                                   P.adv == UGX_ADV_MIN3 || P.adv == UGX_ADV_MIN4);
   const bool cover = P.covers != 0 && a.no_cover == 0;
+  // with `cover` (every match start passes the candidate test) the viability table alone may name the positions worth an
+  // attempt: taken, region by region, when a measurement shows it at least as selective as the candidate masks
+  bool via_only = false;
   const uint64_t limit = __ldcg(a.tail); // spans own [0, limit): the last line belongs to the final kernel
   const uint64_t nregions = (limit + SC_REGION - 1) / SC_REGION;
   const uint64_t total_warps = static_cast<uint64_t>(gridDim.x) * NWARPS;
@@ -336,7 +338,9 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
     // The viability table costs two lookups per byte.  The lazy form lives on it; the mask form measures on the first
     // span of every region how many attempts it spares and keeps it only where that pays (a warp-round of attempts).
     // (the measurement is repeated every eighth region of a warp; in between its last answer stands)
-    const bool probe_now = via.on && !lazy && (probe_tick++ & 7u) == 0;
+    const bool probe_now = via.on && !lazy_fam && (probe_tick++ & 7u) == 0;
+    const bool lazy = lazy_fam || (via_only && !probe_now);
+    const bool mask_lb = has_lb && !lazy;
     bool via_r = via.on && (lazy || probe_now || via_keep);
     bool probing = probe_now;
     SpanMasks cur = eval_masks(t, P, T, s_flags, via, rb + static_cast<int64_t>(s) * SP_SPAN + lane * 16, limit, !lazy, mask_lb, via_r);
@@ -393,6 +397,7 @@ span_scan_kernel(const __grid_constant__ DevPattern P, const uint8_t* __restrict
         {
           probing = false;
           via_keep = __reduce_add_sync(0xffffffffu, __popc(a16 & ~cur.via)) >= 32u;
+          via_only = cover && via_keep && __reduce_add_sync(0xffffffffu, __popc(cur.via & ~a16)) <= 16u;
           via_r = via_keep;
         }
         a16 &= cur.via; // a position that cannot start a match needs no attempt (its D is 0 either way)
