@@ -173,14 +173,18 @@ class B200Matcher : public reflex::Matcher {
     const uint32_t flags = (opt_.N ? UGX_OPT_N : 0u) | (opt_.W ? UGX_OPT_W : 0u);
     const char *dev = getenv("UGREP_B200_DEVICE");
     device_ = dev != NULL ? atoi(dev) : 0;
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     const int rc = ugx_pattern_create(pat.opc_, pat.nop_, &pf, flags, device_, &shared_->pattern);
     if (rc == UGX_E_UNSUPPORTED)
       return unsupported(ugx_last_error());
     if (rc != UGX_OK)
       throw std::runtime_error(std::string("ugrep-b200: ") + ugx_last_error());
+    const std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
     new_scanner();
     if (env_set("UGREP_B200_VERBOSE"))
-      fprintf(stderr, "ugrep-b200: pattern served by libugrep_b200 (device %d)\n", device_);
+      fprintf(stderr, "ugrep-b200: pattern served by libugrep_b200 (device %d; CUDA context + pattern upload %.3f s, scanner %.3f s)\n",
+              device_, std::chrono::duration<double>(t1 - t0).count(),
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
   }
 
   void unsupported(const char *why)
