@@ -119,7 +119,7 @@ def test_covers_flag_agrees_with_the_oracle(name):
         if len(a) < 40:
             continue
         cand = op.candidates(a)
-        for p in np.flatnonzero(~cand[:len(a) - 32])[:1500]:
+        for p in np.flatnonzero(~cand[:len(a) - 32])[:6000]:
             cap, ln = op.match_at(a, int(p))
             assert not (cap and ln), (name, int(p))
             checked += 1
@@ -129,6 +129,7 @@ def test_covers_flag_agrees_with_the_oracle(name):
 def test_covers_is_proven_for_the_word_list_and_refused_for_config3():
     pat = os.path.join(O.ROOT, "ugrep_b200", "patterns")
     assert describe(os.path.join(pat, "c2.ugxp"))[1].covers == 1   # PMH over min = 4 bytes of a tree DFA
+    assert describe(os.path.join(pat, "c4.ugxp"))[1].covers == 1   # PM4, min = 2: "whatever follows" from the table bits
     assert describe(os.path.join(pat, "c1.ugxp"))[1].covers == 0   # `one`: the predicate is the match itself
     assert describe(os.path.join(pat, "c3.ugxp"))[1].covers == 0   # the prefilter has false negatives
     assert describe(os.path.join(pat, "c5.ugxp"))[1].covers == 0   # look-back: the attempt set is more than cand()

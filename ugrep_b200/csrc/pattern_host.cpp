@@ -657,11 +657,88 @@ struct CoverCheck {
       ok = false;
   }
 
+  // PM4 on a window whose first L bytes (1 <= L <= 3) are p[0..L) and whose other bytes are ANYTHING: the verdict of
+  // predict_match depends on the unknown bytes only through the two table bits of each unknown level, so "passes for
+  // all 4^(4-L) values of those bits" is a sufficient condition for "passes whatever follows"
+  bool pm4_whatever_follows(const uint8_t* p, uint32_t L) const
+  {
+    uint32_t q = pred[p[0]] & 0xc0u;
+    uint32_t h = p[0];
+    if (L >= 2)
+    {
+      h = hash3(h, p[1]);
+      q |= pred[h] & 0x30u;
+    }
+    if (L >= 3)
+    {
+      h = hash3(h, p[2]);
+      q |= pred[h] & 0x0cu;
+    }
+    const uint32_t free_bits = L == 1 ? 0x3fu : L == 2 ? 0x0fu : 0x03u;
+    for (uint32_t v = 0; v <= free_bits; ++v)
+    {
+      const uint32_t qq = q | v;
+      const uint32_t r = ((((((qq >> 2) | qq) >> 2) | qq) >> 1) | qq) & 0xffu;
+      if (r == 0xffu)
+        return false;
+    }
+    return true;
+  }
+
+  // the routines whose interior test is [needle bytes] && PM4 on the window at offset `win`: does s[0..depth) followed by
+  // anything pass?  (sufficient, not necessary)
+  bool passes_whatever_follows(uint32_t depth) const
+  {
+    uint32_t win = 0;
+    switch (adv)
+    {
+      case UGX_ADV_PMA: break;
+      case UGX_ADV_PIN_ONE:
+        if (!in(pin_a, s[0]))
+          return false;
+        break;
+      case UGX_ADV_PIN1_ONE:
+        if (s[0] != pf.chr[0])
+          return false;
+        break;
+      case UGX_ADV_PIN_PMA:
+        if (pf.lcp >= depth || pf.lcs >= depth || !in(pin_a, s[pf.lcp]) || !in(pin_b, s[pf.lcs]))
+          return false;
+        break;
+      case UGX_ADV_PIN1_PMA:
+        if (pf.lcp >= depth || pf.lcs >= depth || s[pf.lcp] != pf.chr[0] || s[pf.lcs] != pf.chr[1])
+          return false;
+        break;
+      case UGX_ADV_CHAR_PMA:
+        if (s[0] != pf.chr[0])
+          return false;
+        win = 1;
+        break;
+      case UGX_ADV_STRING_PMA:
+        if (depth < pf.len || !literal())
+          return false;
+        win = pf.len;
+        break;
+      default: return false;
+    }
+    if (depth <= win || depth >= win + 4)
+      return false;
+    return pm4_whatever_follows(s + win, depth - win);
+  }
+
   // every completion of s[0..depth) to `extent` bytes
   void pad(uint32_t depth)
   {
     if (depth == extent)
       return leaf();
+    if (passes_whatever_follows(depth))
+    {
+      if (budget == 0)
+        ok = false;
+      else
+        --budget;
+      return;
+    }
     if (extent - depth > 2)
     {
       ok = false; // 2^24 completions and more: not enumerated
