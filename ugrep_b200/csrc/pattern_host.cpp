@@ -719,6 +719,28 @@ struct CoverCheck {
           return false;
         win = pf.len;
         break;
+      case UGX_ADV_MIN1:
+      case UGX_ADV_MIN2:
+      case UGX_ADV_MIN3:
+      {
+        // bitap step j reads the byte pair (j, j + 1): known bytes as they are, the first unknown byte as all 256 values
+        const uint32_t steps = adv == UGX_ADV_MIN1 ? 1 : adv == UGX_ADV_MIN2 ? 2 : 3;
+        for (uint32_t j = 0; j < steps; ++j)
+        {
+          if (j >= depth)
+            return false;
+          if (j + 1 < depth)
+          {
+            if (tapbit(s + j, j))
+              return false;
+          }
+          else
+            for (uint32_t b = 0; b < 256; ++b)
+              if ((pf.tap[(s[j] ^ (b << 6)) & (UGX_BTAP - 1)] >> j) & 1u)
+                return false;
+        }
+        break;
+      }
       default: return false;
     }
     if (depth <= win || depth >= win + 4)
