@@ -177,26 +177,27 @@ __device__ __forceinline__ bool in_attempt_set(const Text& t, const DevPattern& 
 __device__ __forceinline__ uint32_t longest_in_span(const DevPattern& P, const Stepper& step, const uint8_t* __restrict__ sp,
                                                     uint32_t off, uint32_t rel_end, uint32_t& bad)
 {
-  const uint32_t first_acc = P.first_acc;
-  uint32_t state = 0, best = 0, pp = off;
+  const uint32_t first_acc = P.first_acc, first_leaf = P.first_leaf;
+  uint32_t state = 0, pp = off;
+  // States are numbered so that [first_acc, first_leaf) accept and have byte edges, and ids >= first_leaf have no byte
+  // edges (the interpreter halts there before reading; accepting unless a dead end): the walk only remembers the last
+  // state of either kind and where it was, the accept word is looked up once, afterwards.
+  uint32_t acc_state = 0, acc_len = 0, leaf_state = 0, leaf_len = 0;
   bool stop = false;
-  // nx >= first_acc: dead, accepting, or without outgoing edges (the interpreter halts there before reading)
-  auto special = [&](uint32_t nx) {
+  auto special = [&](uint32_t nx) { // nx >= first_acc
     if (nx == D_DEAD)
-    {
       stop = true;
-      return;
-    }
-    const uint32_t acc = __ldg(P.accept + nx);
-    if ((acc & 0x7fffffffu) != 0)
+    else if (nx >= first_leaf)
     {
-      const uint32_t len = pp - off;
-      if (len >= SP_LONG || (acc & 0x7fffffffu) >= 0x8000u)
-        bad |= 2u;
-      best = ((acc & 0x7fffu) << 16) | (len & 0xffffu);
-    }
-    if ((acc & 0x80000000u) != 0)
+      leaf_state = nx;
+      leaf_len = pp - off;
       stop = true;
+    }
+    else
+    {
+      acc_state = nx;
+      acc_len = pp - off;
+    }
   };
   if (off + 12 <= rel_end)
   {
@@ -224,6 +225,24 @@ __device__ __forceinline__ uint32_t longest_in_span(const DevPattern& P, const S
     if (nx >= first_acc)
       special(nx);
     state = nx;
+  }
+  uint32_t best = 0;
+  if (leaf_state != 0)
+  {
+    const uint32_t acc = __ldg(P.accept + leaf_state) & 0x7fffffffu;
+    if (acc != 0)
+    {
+      if (leaf_len >= SP_LONG || acc >= 0x8000u)
+        bad |= 2u;
+      best = ((acc & 0x7fffu) << 16) | (leaf_len & 0xffffu);
+    }
+  }
+  if (best == 0 && acc_state != 0)
+  {
+    const uint32_t acc = __ldg(P.accept + acc_state) & 0x7fffffffu;
+    if (acc_len >= SP_LONG || acc >= 0x8000u)
+      bad |= 2u;
+    best = ((acc & 0x7fffu) << 16) | (acc_len & 0xffffu);
   }
   if (best == 0 && pp >= rel_end)
     bad |= 1u;
