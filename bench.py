@@ -296,11 +296,13 @@ def main():
     logical_bytes = block.size * reps_total         # the whole job
     expect_total = t1.matches * reps_total          # counts are additive over line-aligned pieces
 
+    gather = sharding.CountExchange("cuda") if world > 1 else None
+
     def exchange(t):
         if world == 1:
             return t.matches
         nl = t.newlines if t.flags & 1 else shard_newlines
-        return sum(c[0] for c in sharding.all_gather_counts(t.matches, nl, device="cuda"))
+        return sum(c[0] for c in gather(t.matches, nl))
 
     # (the streaming `-c` kernels do not count newlines unless asked: the shard's newline count comes from nlcount, once)
     shard_newlines = sc.count_newlines(corpus_dev).newlines if world > 1 else 0
@@ -421,6 +423,7 @@ def main():
             t = ostep(od)
         kms = []
         nsteps = 5
+        ogather = sharding.CountExchange("cuda") if sharded else None
         if sharded:
             barrier()
         else:
@@ -433,7 +436,7 @@ def main():
             kms.append(t.kernel_ms)
             if sharded:
                 # the path's one exchange step, inside the timed region: per-shard {matches, newlines} -> totals, bases
-                counts = sharding.all_gather_counts(t.matches, t.newlines, device="cuda")
+                counts = ogather(t.matches, t.newlines)
         a1.record()
         torch.cuda.synchronize()
         oms = a0.elapsed_time(a1)

@@ -62,6 +62,7 @@ def _worker(rank, world, port, q):
         shard = data[cuts[rank]:cuts[rank + 1]]
         rec = op.find_all(shard)
         counts = sharding.all_gather_counts(len(rec), int((shard == 10).sum()))
+        assert sharding.CountExchange("cpu")(len(rec), int((shard == 10).sum())) == counts  # the loop form of the same exchange
         bases = sharding.bases_from_counts(counts, cuts)
         first_match, base_line, base_off = bases[rank]
         rec = rec.copy()

@@ -52,6 +52,33 @@ def all_gather_counts(matches: int, newlines: int, device=None) -> list[tuple[in
     return [(int(v[0]), int(v[1])) for v in allv]
 
 
+class CountExchange:
+    """all_gather_counts() for a loop: the same collective with its buffers allocated once (one small host-to-device
+    copy, one all-gather into a tensor, one read back per call instead of a dozen tiny tensor operations)"""
+
+    def __init__(self, device="cuda"):
+        import torch
+        import torch.distributed as dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.device = device
+        if self.world > 1:
+            pinned = str(device).startswith("cuda")
+            self.host = torch.zeros(2, dtype=torch.int64, pin_memory=pinned)
+            self.mine = torch.zeros(2, dtype=torch.int64, device=device)
+            self.all = torch.zeros(2 * self.world, dtype=torch.int64, device=device)
+
+    def __call__(self, matches: int, newlines: int) -> list[tuple[int, int]]:
+        if self.world == 1:
+            return [(int(matches), int(newlines))]
+        import torch.distributed as dist
+        self.host[0] = int(matches)
+        self.host[1] = int(newlines)
+        self.mine.copy_(self.host, non_blocking=True)
+        dist.all_gather_into_tensor(self.all, self.mine)
+        v = self.all.tolist()
+        return [(v[2 * r], v[2 * r + 1]) for r in range(self.world)]
+
+
 def tiled_cuts(block: np.ndarray, reps: int, world: int) -> list[int]:
     """line_aligned_cuts() for the logical corpus ``block`` repeated ``reps`` times (``block`` ends with a newline),
     computed from the block alone: the nominal cut n*r/world moves forward to the end of the line it falls in."""
