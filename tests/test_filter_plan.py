@@ -148,3 +148,45 @@ def test_dfa_export_shapes_of_the_configs():
     for info in (c2, c4, c1):
         assert 1 <= info.first_acc <= info.first_leaf <= info.states
         assert info.table_bytes == info.states * info.classes * 2
+
+
+def test_covers_is_sound_on_random_word_lists(tmp_path):
+    """word lists compiled by the library itself (min lengths 1..8: the PM4, bitap and hashed-predictor routines):
+    wherever the proof says `covers`, no position outside the oracle's candidate set starts a match — on text made of
+    the words, their prefixes and noise"""
+    from ugrep_b200 import api
+    rng = np.random.default_rng(2024)
+    proven = 0
+    for trial in range(40):
+        alpha = [b"ab", b"abcdefgh", b"etaoinshr", b"0123456789-"][trial % 4]
+        lo = int(rng.integers(1, 7))
+        words = set()
+        while len(words) < int(rng.choice([1, 2, 5, 20, 100])):
+            n = int(rng.integers(lo, lo + 5))
+            words.add(bytes(int(alpha[int(i)]) for i in rng.integers(0, len(alpha), size=n)))
+        words = sorted(words)
+        try:
+            opc, pf = api.compile_words(words)
+        except api.UgxError:
+            continue
+        path = str(tmp_path / ("w%d.ugxp" % trial))
+        api.write_ugxp(path, opc, pf)
+        rc, info, _ = describe(path)
+        assert rc == 0
+        if not info.covers or info.advance == 0:
+            continue
+        proven += 1
+        op = O.OraclePattern(path)
+        parts = []
+        for _ in range(400):
+            k = int(rng.integers(0, 4))
+            w = words[int(rng.integers(0, len(words)))]
+            parts.append(w if k == 0 else w[:int(rng.integers(0, len(w) + 1))] if k == 1 else
+                         bytes(int(alpha[int(i)]) for i in rng.integers(0, len(alpha), size=int(rng.integers(1, 6)))) if k == 2
+                         else rng.choice([b" ", b"\n", b"x"]))
+        a = np.frombuffer(b"".join(parts) + b"\n" + b" " * 40, dtype=np.uint8)
+        cand = op.candidates(a)
+        for p in np.flatnonzero(~cand[:len(a) - 32]):
+            cap, ln = op.match_at(a, int(p))
+            assert not (cap and ln), (trial, words[:5], int(p))
+    assert proven >= 10

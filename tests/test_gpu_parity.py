@@ -475,13 +475,11 @@ def test_word_list_compiled_by_the_library_itself(gpu):
 def test_word_list_too_big_for_shared_memory(gpu, tmp_path):
     """3 000 words: a 400 KB transition table, read from global memory (Stepper's unstaged form) by the streaming count,
     the span kernels and the records path; oracle on the same compiled pattern, plus a plain substring count"""
-    import struct
     api, sc = gpu
     words = corpus.words_list(11, 3000)
     opc, pf = api.compile_words(words)
     path = str(tmp_path / "w3000.ugxp")
-    with open(path, "wb") as f:
-        f.write(b"UGXP\x01\x00\x00\x00" + struct.pack("<4I", len(opc), 0, len(pf), 0) + pf + np.asarray(opc, dtype="<u4").tobytes())
+    api.write_ugxp(path, opc, pf)
     op = O.OraclePattern(path)
     pat = api.Pattern.words(words, 0)
     assert pat.info["table_in_smem"] == 0 and pat.info["table_bytes"] > 300000

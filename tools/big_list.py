@@ -7,7 +7,6 @@ what happens when the transition table no longer fits in shared memory (tables >
 """
 import argparse
 import os
-import struct
 import sys
 import tempfile
 
@@ -17,11 +16,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from ugrep_b200 import api, corpus  # noqa: E402
-
-
-def write_ugxp(path, opc, pf, flags=0):
-    with open(path, "wb") as f:
-        f.write(b"UGXP\x01\x00\x00\x00" + struct.pack("<4I", len(opc), 0, len(pf), flags) + pf + np.asarray(opc, dtype="<u4").tobytes())
 
 
 def main():
@@ -56,7 +50,7 @@ def main():
         got = sc.count_lines(pat, torch.from_numpy(block[:4 << 20].copy()).cuda()).matches
         with tempfile.TemporaryDirectory() as d:
             p = os.path.join(d, "w.ugxp")
-            write_ugxp(p, opc, pf)
+            api.write_ugxp(p, opc, pf)
             want = O.OraclePattern(p).count_lines(block[:4 << 20])
         print("%5d words: table %7d B, in smem %d, %7.1f GB/s, 4 MiB check gpu %d oracle %d %s"
               % (count, info["table_bytes"], info["table_in_smem"], dev.numel() / best / 1e6, got, want,

@@ -319,6 +319,14 @@ def read_ugxp(path: str):
     return opc, pf, int(flags)
 
 
+def write_ugxp(path: str, opc, pf: bytes, flags: int = 0) -> None:
+    """the inverse of read_ugxp: a UGXP pattern file from compiled words (no regex text is stored)"""
+    import struct
+    with open(path, "wb") as f:
+        f.write(b"UGXP\x01\x00\x00\x00" + struct.pack("<4I", len(opc), 0, len(pf), int(flags)) + bytes(pf)
+                + np.asarray(opc, dtype="<u4").tobytes())
+
+
 class Sharded:
     """One process, several GPUs: ugx_sharded_* (line-aligned shards of one host buffer, one device each)."""
 
