@@ -415,7 +415,7 @@ def test_span_kernels_hand_over_what_they_cannot_vouch_for(gpu):
     api, sc = gpu
     cases = [
         ("dotstar", b"x" * 20000 + b"a" + b"y" * 40000 + b"b zz a b\n" + b"a b\n" * 10),
-        ("pin_pma_lb", b"the s" + b"a" * 50000 + b"ing sing\nsing song\n"),
+        ("pin_pma_lb", b"the s" + b"a" * 1100000 + b"ing sing\nsing song\n"),
         ("dotstar", b"a" + b"q" * 70000 + b"b\n" + b"ab\n" * 5),
         ("c5", b"x" * 100000 + b" ERROR 555-12"),
     ]

@@ -60,6 +60,8 @@ def main():
             pats[name] = (api.Pattern.load(G.pattern_path(name), 0), O.OraclePattern(G.pattern_path(name)))
         pat, op = pats[name]
         data = make_text(rng, blocks)
+        if os.environ.get("UGX_FUZZ_TRACE"):
+            print("case %d %s %d bytes t=%.1f" % (n, name, len(data), time.time() - t0), flush=True)
         want = op.find_all(data)
         rec, tot = sc.find_all(pat, data)
         kernels[tot.kernel] = kernels.get(tot.kernel, 0) + 1

@@ -56,7 +56,9 @@ constexpr uint32_t SP_SPAN = 512;
 constexpr int SP_SPANS = SC_REGION / SP_SPAN; // spans per region
 constexpr uint32_t SP_LONG = 0xffffu;         // D(p) is kept in 16 bits
 constexpr uint64_t SP_NO_V = ~0ull;           // region needs no validation (its chain starts after a newline)
-constexpr uint32_t SP_FAR_SPANS = 64;         // longest look-ahead over a run of look-back bytes (32 KiB)
+constexpr uint32_t SP_FAR_SPANS = 2048;       // longest look-ahead over a run of look-back bytes (1 MiB): beyond it the
+                                              // buffer goes to the line-at-a-time kernels, where ONE thread walks the line —
+                                              // far worse than looking ahead
 
 struct SpanMasks {
   uint32_t cand, cbk, nl, via; // 16 bits each: bit k = byte k of the lane's chunk
