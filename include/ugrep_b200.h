@@ -187,6 +187,11 @@ int  ugx_compile_literal(const uint8_t *literal, uint32_t len, uint32_t *opc, ui
  * that part of the analysis is not restated). */
 int  ugx_compile_words(const uint8_t *const *words, const uint32_t *lens, uint32_t nwords, uint32_t *opc, uint32_t cap,
                        uint32_t *nop, ugx_prefilter *pf);
+/* the same with options: UGX_COMPILE_ICASE = `ugrep -F -i -f words.txt` (the strings are lowered as they enter the tree
+ * and every edge on a lowercase ASCII letter gets an uppercase twin, lib/pattern.cpp:286-311, 834) */
+enum { UGX_COMPILE_ICASE = 1 };
+int  ugx_compile_words_ex(const uint8_t *const *words, const uint32_t *lens, uint32_t nwords, uint32_t options,
+                          uint32_t *opc, uint32_t cap, uint32_t *nop, ugx_prefilter *pf);
 /* host only (no device needed): DFA export + filter plan of a compiled pattern */
 int  ugx_plan_describe(const uint32_t *opc, uint32_t nop, const ugx_prefilter *pf, uint32_t matcher_flags,
                        ugx_plan_info *out);

@@ -91,6 +91,22 @@ def test_wordlist_compile_equals_committed_reference_output():
     assert a[0].tolist() == b[0].tolist() and a[1] == b[1]
 
 
+def test_wordlist_compile_icase_equals_committed_reference_output():
+    """`-F -i -f LIST`: strings lowered into the tree, an uppercase twin for every lowercase edge (tools/make_icase_golden.py)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_icase_golden", os.path.join(O.ROOT, "tools", "make_icase_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    pf, opc = parts(os.path.join(O.ROOT, "tests", "golden", "words_icase.ugxp"))
+    got_opc, got_pf = api.compile_words(mod.WORDS, icase=True)
+    assert got_opc.tolist() == opc.tolist()
+    assert got_pf == pf
+    # and the compiled pattern matches case-insensitively in the oracle
+    op = O.OraclePattern(os.path.join(O.ROOT, "tests", "golden", "words_icase.ugxp"))
+    text = b"an ERROR here\nwarn: Fatal TIMEOUT2\nnothing\nSHERLOCK holmes and NA\xc3\xafVE\n"
+    assert op.count_lines(text) == 3 and op.count_matches(text) == 6
+
+
 def test_wordlist_compile_scope():
     for bad in ([b""], [b"ok", b""], [b"a\nb"], [b"a\x00"]):
         with pytest.raises(api.UgxError) as e:
@@ -121,19 +137,23 @@ def _random_lists():
 
 
 @pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref (the built reference) is not present")
-def test_wordlist_compile_equals_the_live_reference_on_random_lists(tmp_path):
-    """byte equality of opcode words and prefilter block with `refscan dump -F -f`; a list the library refuses must be
-    one for which the reference's analysis cut the DFA (cut_ != 0), and only those"""
+@pytest.mark.parametrize("icase", [False, True])
+def test_wordlist_compile_equals_the_live_reference_on_random_lists(tmp_path, icase):
+    """byte equality of opcode words and prefilter block with `refscan dump -F [-i] -f`; a list the library refuses must
+    be one for which the reference's analysis cut the DFA (cut_ != 0), and only those"""
     wf = tmp_path / "w.txt"
     out = str(tmp_path / "p.ugxp")
     n_ok = n_cut = 0
+    rng = np.random.default_rng(9)
     for words in _random_lists():
+        if icase:  # mixed case in the list itself
+            words = [bytes((c - 32 if (97 <= c <= 122 and rng.random() < 0.3) else c) for c in w) for w in words]
         wf.write_bytes(b"\n".join(words) + b"\n")
-        O.ref_dump(["-F", "-f", str(wf)], out)
+        O.ref_dump(["-F", "-i", "-f", str(wf)] if icase else ["-F", "-f", str(wf)], out)
         pf, opc = parts(out)
         cut = struct.unpack_from("<12I", pf, 0)[11]
         try:
-            got_opc, got_pf = api.compile_words(words)
+            got_opc, got_pf = api.compile_words(words, icase=icase)
         except api.UgxError as e:
             assert e.code == 2 and cut != 0, words[:3]
             n_cut += 1

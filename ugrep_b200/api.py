@@ -27,7 +27,7 @@ ADVANCE_NAMES = ["none", "pin1_one", "pin1_pma", "pin1_pmh", "pin_one", "pin_pma
 
 EXPORTS = ["ugx_last_error", "ugx_kernel_name", "ugx_plan_describe", "ugx_abi_version", "ugx_pattern_create", "ugx_pattern_load", "ugx_pattern_info_get",
            "ugx_pattern_destroy", "ugx_scanner_create", "ugx_scanner_destroy", "ugx_count_lines", "ugx_count_matches",
-           "ugx_viability_describe", "ugx_check_text", "ugx_compile_literal", "ugx_compile_words", "ugx_count_batch", "ugx_sharded_create", "ugx_sharded_destroy", "ugx_sharded_set_option", "ugx_sharded_scan", "ugx_sharded_last_error", "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_scanner_set_option", "ugx_count_newlines"]
+           "ugx_viability_describe", "ugx_check_text", "ugx_compile_literal", "ugx_compile_words", "ugx_compile_words_ex", "ugx_count_batch", "ugx_sharded_create", "ugx_sharded_destroy", "ugx_sharded_set_option", "ugx_sharded_scan", "ugx_sharded_last_error", "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_scanner_set_option", "ugx_count_newlines"]
 
 
 class UgxError(RuntimeError):
@@ -131,11 +131,12 @@ def compile_literal(text: bytes):
     return opc[:nop.value].copy(), pf.raw
 
 
-def compile_words(words):
-    """(opcode words, ugx_prefilter bytes) of a list of fixed strings (`ugrep -F -f FILE`), as the reference's compiler
-    would produce them; UgxError code 2 when the list is outside the restated part of the compiler"""
+def compile_words(words, icase: bool = False):
+    """(opcode words, ugx_prefilter bytes) of a list of fixed strings (`ugrep -F [-i] -f FILE`), as the reference's
+    compiler would produce them; UgxError code 2 when the list is outside the restated part of the compiler"""
     L = lib()
-    L.ugx_compile_words.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p]
+    L.ugx_compile_words_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
+                                       C.POINTER(C.c_uint32), C.c_void_p]
     ws = [bytes(w) for w in words]
     ptrs = (C.c_char_p * len(ws))(*ws)
     lens = (C.c_uint32 * len(ws))(*[len(w) for w in ws])
@@ -143,7 +144,7 @@ def compile_words(words):
     opc = np.zeros(cap, dtype=np.uint32)
     nop = C.c_uint32()
     pf = C.create_string_buffer(PREFILTER_BYTES)
-    rc = L.ugx_compile_words(ptrs, lens, len(ws), opc.ctypes.data, cap, C.byref(nop), pf)
+    rc = L.ugx_compile_words_ex(ptrs, lens, len(ws), 1 if icase else 0, opc.ctypes.data, cap, C.byref(nop), pf)
     if rc != 0:
         raise UgxError(rc, "ugx_compile_words: list outside its scope" if rc == 2 else "ugx_compile_words failed")
     return opc[:nop.value].copy(), pf.raw
@@ -171,9 +172,9 @@ class Pattern:
         return cls(h, device)
 
     @classmethod
-    def words(cls, words, device: int = 0) -> "Pattern":
-        """`ugrep -F -f FILE`: compiled by the library itself (ugx_compile_words)"""
-        opc, pf = compile_words(words)
+    def words(cls, words, device: int = 0, icase: bool = False) -> "Pattern":
+        """`ugrep -F [-i] -f FILE`: compiled by the library itself (ugx_compile_words_ex)"""
+        opc, pf = compile_words(words, icase)
         h = C.c_void_p()
         _check(lib().ugx_pattern_create(opc.ctypes.data, len(opc), pf, 0, device, C.byref(h)))
         return cls(h, device)

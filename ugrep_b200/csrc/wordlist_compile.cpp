@@ -547,8 +547,15 @@ int encode(std::vector<Node>& t, std::vector<uint32_t>& opc)
 extern "C" int ugx_compile_words(const uint8_t* const* words, const uint32_t* lens, uint32_t nwords, uint32_t* opc, uint32_t cap,
                                  uint32_t* nop, ugx_prefilter* pf)
 {
-  if (words == nullptr || lens == nullptr || nop == nullptr || pf == nullptr || nwords == 0)
+  return ugx_compile_words_ex(words, lens, nwords, 0, opc, cap, nop, pf);
+}
+
+extern "C" int ugx_compile_words_ex(const uint8_t* const* words, const uint32_t* lens, uint32_t nwords, uint32_t options,
+                                    uint32_t* opc, uint32_t cap, uint32_t* nop, ugx_prefilter* pf)
+{
+  if (words == nullptr || lens == nullptr || nop == nullptr || pf == nullptr || nwords == 0 || (options & ~1u) != 0)
     return UGX_E_INVALID;
+  const bool icase = (options & UGX_COMPILE_ICASE) != 0;
   try
   {
     // ---- the tree, in the order given
@@ -560,9 +567,11 @@ extern "C" int ugx_compile_words(const uint8_t* const* words, const uint32_t* le
       uint32_t r = 0;
       for (uint32_t i = 0; i < lens[w]; ++i)
       {
-        const uint32_t c = words[w][i];
+        uint32_t c = words[w][i];
         if (c == 0 || c == '\n' || c == '\r')
           return UGX_E_UNSUPPORTED;
+        if (icase && c >= 'A' && c <= 'Z')
+          c += 'a' - 'A'; // (lib/pattern.cpp:834)
         auto it = t[r].edge.find(c);
         if (it == t[r].edge.end())
         {
@@ -577,6 +586,14 @@ extern "C" int ugx_compile_words(const uint8_t* const* words, const uint32_t* le
       if (t[r].accept == 0)
         t[r].accept = w + 1;
     }
+    if (icase)
+      for (Node& s : t) // an uppercase twin for every edge on a lowercase letter (lib/pattern.cpp:292-309)
+        for (uint32_t c = 'a'; c <= 'z'; ++c)
+        {
+          auto it = s.edge.find(c);
+          if (it != s.edge.end())
+            s.edge[c - ('a' - 'A')] = it->second;
+        }
     memset(pf, 0, sizeof(*pf));
     // ---- analysis
     if (analysis_cuts(t, *pf))
