@@ -107,6 +107,24 @@ def test_wordlist_compile_icase_equals_committed_reference_output():
     assert op.count_lines(text) == 3 and op.count_matches(text) == 6
 
 
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref (the built reference) is not present")
+def test_single_literal_icase_equals_the_live_reference(tmp_path):
+    """`-F -i 'literal'`: the word-list compiler on a list of one"""
+    out = str(tmp_path / "p.ugxp")
+    rng = np.random.default_rng(4)
+    n = 0
+    for _ in range(120):
+        lit = bytes(int(x) for x in rng.choice(list(b"abcXYZ eE0-_.:"), size=int(rng.integers(1, 20))))
+        if lit.strip() != lit:
+            continue
+        O.ref_dump(["-F", "-i", "-e", lit.decode()], out)
+        pf, opc = parts(out)
+        got_opc, got_pf = api.compile_words([lit], icase=True)
+        assert got_opc.tolist() == opc.tolist() and got_pf == pf, lit
+        n += 1
+    assert n >= 60
+
+
 def test_wordlist_compile_scope():
     for bad in ([b""], [b"ok", b""], [b"a\nb"], [b"a\x00"]):
         with pytest.raises(api.UgxError) as e:

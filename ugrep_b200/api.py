@@ -164,9 +164,10 @@ class Pattern:
         return cls(h, device)
 
     @classmethod
-    def literal(cls, text: bytes, device: int = 0) -> "Pattern":
-        """`ugrep -F TEXT`: compiled by the library itself (ugx_compile_literal), no reference binary needed"""
-        opc, pf = compile_literal(text)
+    def literal(cls, text: bytes, device: int = 0, icase: bool = False) -> "Pattern":
+        """`ugrep -F [-i] TEXT`: compiled by the library itself (ugx_compile_literal; with -i the word-list compiler on a
+        list of one), no reference binary needed"""
+        opc, pf = compile_words([text], True) if icase else compile_literal(text)
         h = C.c_void_p()
         _check(lib().ugx_pattern_create(opc.ctypes.data, len(opc), pf, 0, device, C.byref(h)))
         return cls(h, device)
