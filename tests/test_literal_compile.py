@@ -125,6 +125,31 @@ def test_single_literal_icase_equals_the_live_reference(tmp_path):
     assert n >= 60
 
 
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref (the built reference) is not present")
+def test_plain_regex_alternations_compile_like_fixed_strings(tmp_path):
+    """`ugrep [-i] -e A -e B` without -F, no regex operator in A, B: same compiled form (api.compile_plain)"""
+    from ugrep_b200 import corpus
+    out = str(tmp_path / "p.ugxp")
+    rng = np.random.default_rng(6)
+    eng = [w.encode() for w in corpus._ENGLISH]
+    punct = [b"id=7", b"a-b", b"x:y", b"/usr/lib", b"a,b;c", b"u@h", b"#tag", b"50%", b"R&D", b"~x", b"it's", b"<b>", b"say \"hi\"", b"a b"]
+    for k in range(40):
+        words = [bytes(w) for w in rng.choice(eng, size=int(rng.integers(1, 8)), replace=False)]
+        if k % 3 == 0:
+            words.append(punct[k % len(punct)])
+        icase = k % 2 == 1
+        args = ["-i"] if icase else []
+        for w in words:
+            args += ["-e", w.decode()]
+        O.ref_dump(args, out)
+        pf, opc = parts(out)
+        got_opc, got_pf = api.compile_plain(words, icase=icase)
+        assert got_opc.tolist() == opc.tolist() and got_pf == pf, words
+    for bad in (b"a.b", b"x*", b"(a)", b"a|b", b"^a", b"a$", b"a\\b", b"[ab]", b"a{2}", b"a+", b"a?"):
+        with pytest.raises(api.UgxError):
+            api.compile_plain([bad])
+
+
 def test_wordlist_compile_scope():
     for bad in ([b""], [b"ok", b""], [b"a\nb"], [b"a\x00"]):
         with pytest.raises(api.UgxError) as e:

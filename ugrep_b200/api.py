@@ -321,6 +321,21 @@ def read_ugxp(path: str):
     return opc, pf, int(flags)
 
 
+_REGEX_OPERATORS = frozenset(b"\\.[](){}*+?|^$")
+
+
+def compile_plain(patterns, icase: bool = False):
+    """`ugrep [-i] -e A -e B ...` WITHOUT -F, for patterns that contain no regex operator: the reference's parser puts an
+    alternation of plain strings into the same tree DFA as -F does (lib/pattern.cpp:286-311), so the compiled form is
+    that of the fixed-string list (checked against `refscan dump` without -F).  UgxError code 2 for a pattern with an
+    operator: the regex compiler proper is not part of this library."""
+    ps = [bytes(p) for p in patterns]
+    for p in ps:
+        if any(c in _REGEX_OPERATORS for c in p):
+            raise UgxError(2, "compile_plain: %r contains a regex operator" % p)
+    return compile_words(ps, icase)
+
+
 def write_ugxp(path: str, opc, pf: bytes, flags: int = 0) -> None:
     """the inverse of read_ugxp: a UGXP pattern file from compiled words (no regex text is stored)"""
     import struct
