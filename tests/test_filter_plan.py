@@ -165,8 +165,9 @@ def test_covers_is_sound_on_random_word_lists(tmp_path):
             n = int(rng.integers(lo, lo + 5))
             words.add(bytes(int(alpha[int(i)]) for i in rng.integers(0, len(alpha), size=n)))
         words = sorted(words)
+        icase = trial % 5 == 4   # (-i: an uppercase twin for every lowercase edge; the text below mixes the cases)
         try:
-            opc, pf = api.compile_words(words)
+            opc, pf = api.compile_words(words, icase=icase)
         except api.UgxError:
             continue
         path = str(tmp_path / ("w%d.ugxp" % trial))
@@ -184,7 +185,10 @@ def test_covers_is_sound_on_random_word_lists(tmp_path):
             parts.append(w if k == 0 else w[:int(rng.integers(0, len(w) + 1))] if k == 1 else
                          bytes(int(alpha[int(i)]) for i in rng.integers(0, len(alpha), size=int(rng.integers(1, 6)))) if k == 2
                          else rng.choice([b" ", b"\n", b"x"]))
-        a = np.frombuffer(b"".join(parts) + b"\n" + b" " * 40, dtype=np.uint8)
+        text = b"".join(parts)
+        if icase:
+            text = bytes((c - 32 if (97 <= c <= 122 and rng.random() < 0.4) else c) for c in text)
+        a = np.frombuffer(text + b"\n" + b" " * 40, dtype=np.uint8)
         cand = op.candidates(a)
         for p in np.flatnonzero(~cand[:len(a) - 32]):
             cap, ln = op.match_at(a, int(p))
