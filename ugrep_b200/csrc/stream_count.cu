@@ -22,7 +22,6 @@
 //   * the line that is open at the start of a region cannot be resolved locally: the region publishes
 //     three bits (has newline, success before the first newline, success after the last newline) and
 //     the last CTA to finish chains them over all regions.
-#include <cstdio>
 #include "device_pattern.cuh"
 #include "line_match.cuh"
 #include "scan_kernels.hpp"
