@@ -192,6 +192,14 @@ int  ugx_compile_words(const uint8_t *const *words, const uint32_t *lens, uint32
 enum { UGX_COMPILE_ICASE = 1 };
 int  ugx_compile_words_ex(const uint8_t *const *words, const uint32_t *lens, uint32_t nwords, uint32_t options,
                           uint32_t *opc, uint32_t cap, uint32_t *nop, ugx_prefilter *pf);
+/* host only: a REGEX that is an alternation of plain strings — `ugrep [-i] -e 'foo\.bar|baz'` without -F.  The
+ * reference's parser puts such a regex into the same tree DFA as a -F list (lib/pattern.cpp:286-311, 798-866), so this
+ * is ugx_compile_words_ex on the alternatives.  Accepted: bytes other than the operators \ . [ ] ( ) { } * + ? | ^ $,
+ * top-level `|`, a backslash before an operator or one of ! " # % & ' , - / : ; @ ` (that character), \t \f \v \a,
+ * \Q...\E; with UGX_COMPILE_ICASE no byte >= 0x80 outside \Q...\E.  Anything else (classes, groups, repeats, anchors,
+ * \d \w \b \xHH ...) returns UGX_E_UNSUPPORTED: the regex compiler proper is not part of this library.  Alternative i (1-based) is accept index i. */
+int  ugx_compile_plain_regex(const uint8_t *regex, uint32_t len, uint32_t options, uint32_t *opc, uint32_t cap,
+                             uint32_t *nop, ugx_prefilter *pf);
 /* host only (no device needed): DFA export + filter plan of a compiled pattern */
 int  ugx_plan_describe(const uint32_t *opc, uint32_t nop, const ugx_prefilter *pf, uint32_t matcher_flags,
                        ugx_plan_info *out);

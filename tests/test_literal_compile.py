@@ -145,9 +145,42 @@ def test_plain_regex_alternations_compile_like_fixed_strings(tmp_path):
         pf, opc = parts(out)
         got_opc, got_pf = api.compile_plain(words, icase=icase)
         assert got_opc.tolist() == opc.tolist() and got_pf == pf, words
-    for bad in (b"a.b", b"x*", b"(a)", b"a|b", b"^a", b"a$", b"a\\b", b"[ab]", b"a{2}", b"a+", b"a?"):
+    # escapes, \\Q..\\E and top-level alternation inside ONE pattern
+    fixed = [r"a\.b", r"x\*y", r"\(a\)", r"a\|b", r"c:\\dir", r"\[x\]", r"a\+b", r"wh\?", r"\$9", r"\^x", r"a\{2\}", r"tab\there",
+             r"a\-b", r"\Qa.b*\E", r"foo\.bar|baz\.qux", r"one|two|three", r"\Q(x)\E|y\/z", r"na\xc3\xafve".replace(r"\xc3\xaf", "ï")]
+    punct_all = "!\"#%&',-/:;@`"      # escapable; \\~ \\< \\> \\= \\_ \\e are rewritten or rejected by the reference: refused here
+    bare_only = "<=>_~"
+    ops = ".[](){}*+?|^$\\"
+    for k in range(40):
+        alts = []
+        for _ in range(int(rng.integers(1, 5))):
+            w = ""
+            for _ in range(int(rng.integers(1, 9))):
+                r = rng.random()
+                if r < 0.6:
+                    w += chr(int(rng.choice(list(b"abcdexyzAB019"))))
+                elif r < 0.8:
+                    w += "\\" + ops[int(rng.integers(0, len(ops)))]
+                elif r < 0.9:
+                    both = punct_all + bare_only
+                    w += both[int(rng.integers(0, len(both)))]
+                else:
+                    w += "\\" + punct_all[int(rng.integers(0, len(punct_all)))]
+            alts.append(w)
+        fixed.append("|".join(alts))
+    for k, rx in enumerate(fixed):
+        icase = k % 3 == 2 and rx.isascii()   # (-i with non-ASCII letters outside \\Q..\\E: refused, see below)
+        O.ref_dump((["-i"] if icase else []) + ["-e", rx], out)
+        pf, opc = parts(out)
+        got_opc, got_pf = api.compile_plain([rx.encode()], icase=icase)
+        assert got_opc.tolist() == opc.tolist() and got_pf == pf, rx
+    for bad in (b"a.b", b"x*", b"(a)", b"^a", b"a$", b"a\\b", b"a\\d", b"[ab]", b"a{2}", b"a+", b"a?", b"a||b", b"|a", b"\\Qabc",
+                b"a\\x41", b"\\xe9", b"a]", b"a}", b"a\\", b"a\\~b", b"a\\<b", b"a\\eb", b"a\\_b"):
         with pytest.raises(api.UgxError):
             api.compile_plain([bad])
+    with pytest.raises(api.UgxError):
+        api.compile_plain(["naïve".encode()], icase=True)
+    api.compile_plain(["\\Qnaïve\\E".encode()], icase=True)
 
 
 def test_wordlist_compile_scope():

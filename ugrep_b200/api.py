@@ -27,7 +27,7 @@ ADVANCE_NAMES = ["none", "pin1_one", "pin1_pma", "pin1_pmh", "pin_one", "pin_pma
 
 EXPORTS = ["ugx_last_error", "ugx_kernel_name", "ugx_plan_describe", "ugx_abi_version", "ugx_pattern_create", "ugx_pattern_load", "ugx_pattern_info_get",
            "ugx_pattern_destroy", "ugx_scanner_create", "ugx_scanner_destroy", "ugx_count_lines", "ugx_count_matches",
-           "ugx_viability_describe", "ugx_check_text", "ugx_compile_literal", "ugx_compile_words", "ugx_compile_words_ex", "ugx_count_batch", "ugx_sharded_create", "ugx_sharded_destroy", "ugx_sharded_set_option", "ugx_sharded_scan", "ugx_sharded_last_error", "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_scanner_set_option", "ugx_count_newlines"]
+           "ugx_viability_describe", "ugx_check_text", "ugx_compile_literal", "ugx_compile_words", "ugx_compile_words_ex", "ugx_compile_plain_regex", "ugx_count_batch", "ugx_sharded_create", "ugx_sharded_destroy", "ugx_sharded_set_option", "ugx_sharded_scan", "ugx_sharded_last_error", "ugx_find_all", "ugx_find_all_device", "ugx_scanner_fetch", "ugx_scanner_set_option", "ugx_count_newlines"]
 
 
 class UgxError(RuntimeError):
@@ -321,19 +321,23 @@ def read_ugxp(path: str):
     return opc, pf, int(flags)
 
 
-_REGEX_OPERATORS = frozenset(b"\\.[](){}*+?|^$")
-
-
 def compile_plain(patterns, icase: bool = False):
-    """`ugrep [-i] -e A -e B ...` WITHOUT -F, for patterns that contain no regex operator: the reference's parser puts an
-    alternation of plain strings into the same tree DFA as -F does (lib/pattern.cpp:286-311), so the compiled form is
-    that of the fixed-string list (checked against `refscan dump` without -F).  UgxError code 2 for a pattern with an
-    operator: the regex compiler proper is not part of this library."""
-    ps = [bytes(p) for p in patterns]
-    for p in ps:
-        if any(c in _REGEX_OPERATORS for c in p):
-            raise UgxError(2, "compile_plain: %r contains a regex operator" % p)
-    return compile_words(ps, icase)
+    """`ugrep [-i] -e A -e B ...` WITHOUT -F, for patterns that are alternations of plain strings (escaped operators,
+    \\t, \\Q..\\E and top-level | allowed): ugx_compile_plain_regex on the patterns joined with |, as ugrep joins
+    them.  UgxError code 2 for anything else: the regex compiler proper is not part of this library."""
+    L = lib()
+    L.ugx_compile_plain_regex.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
+                                          C.c_void_p]
+    regex = b"|".join(bytes(p) for p in patterns)
+    cap = 4 * (len(regex) + 2 * (regex.count(b"|") + 1)) + 16
+    opc = np.zeros(cap, dtype=np.uint32)
+    nop = C.c_uint32()
+    pf = C.create_string_buffer(PREFILTER_BYTES)
+    rc = L.ugx_compile_plain_regex(regex, len(regex), 1 if icase else 0, opc.ctypes.data, cap, C.byref(nop), pf)
+    if rc != 0:
+        raise UgxError(rc, "ugx_compile_plain_regex: not an alternation of plain strings" if rc == 2 else
+                       "ugx_compile_plain_regex failed")
+    return opc[:nop.value].copy(), pf.raw
 
 
 def write_ugxp(path: str, opc, pf: bytes, flags: int = 0) -> None:

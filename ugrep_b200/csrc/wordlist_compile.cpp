@@ -648,3 +648,82 @@ extern "C" int ugx_compile_words_ex(const uint8_t* const* words, const uint32_t*
     return UGX_E_NOMEM;
   }
 }
+
+// a regex without operators other than top-level alternation and escapes of single characters: the strings it stands for
+extern "C" int ugx_compile_plain_regex(const uint8_t* regex, uint32_t len, uint32_t options, uint32_t* opc, uint32_t cap,
+                                       uint32_t* nop, ugx_prefilter* pf)
+{
+  if (regex == nullptr || nop == nullptr || pf == nullptr)
+    return UGX_E_INVALID;
+  try
+  {
+    std::vector<std::vector<uint8_t>> alts(1);
+    bool quoted = false;
+    for (uint32_t i = 0; i < len; ++i)
+    {
+      const uint8_t c = regex[i];
+      if (quoted)
+      {
+        if (c == '\\' && i + 1 < len && regex[i + 1] == 'E')
+        {
+          quoted = false;
+          ++i;
+        }
+        else
+          alts.back().push_back(c);
+        continue;
+      }
+      if (c == '|')
+      {
+        alts.emplace_back();
+        continue;
+      }
+      if (c == '\\')
+      {
+        if (i + 1 >= len)
+          return UGX_E_UNSUPPORTED;
+        const uint8_t e = regex[++i];
+        if (e == 'Q')
+          quoted = true;
+        else if (e == 't')
+          alts.back().push_back('\t');
+        else if (e == 'f')
+          alts.back().push_back('\f');
+        else if (e == 'v')
+          alts.back().push_back('\v');
+        else if (e == 'a')
+          alts.back().push_back('\a');
+        else if (e != 0 && strchr("\\.[](){}*+?|^$!\"#%&',-/:;@`", e) != nullptr)
+          alts.back().push_back(e); // an escaped operator / punctuation character stands for itself
+        else
+          return UGX_E_UNSUPPORTED; // \d \w \s \b \< \p{..} \1 ...: classes, anchors, back-references — and the escapes
+                                    // the reference's converter rewrites (\~ \e \xHH ...), which leave its tree path
+        continue;
+      }
+      if (c == '.' || c == '[' || c == ']' || c == '(' || c == ')' || c == '{' || c == '}' || c == '*' || c == '+' || c == '?' ||
+          c == '^' || c == '$')
+        return UGX_E_UNSUPPORTED; // (a bare ] or } is an ordinary character to the reference's parser in most places, an
+                                  // error in some: refused, write \\] \\})
+      if (c >= 0x80 && (options & UGX_COMPILE_ICASE) != 0)
+        return UGX_E_UNSUPPORTED; // the reference's converter folds the case of non-ASCII letters into classes (not so
+                                  // inside \\Q..\\E, which is how -F -i passes them)
+      alts.back().push_back(c);
+    }
+    if (quoted)
+      return UGX_E_UNSUPPORTED;
+    std::vector<const uint8_t*> ptrs;
+    std::vector<uint32_t> lens;
+    for (const auto& a : alts)
+    {
+      if (a.empty())
+        return UGX_E_UNSUPPORTED; // an empty alternative matches the empty string
+      ptrs.push_back(a.data());
+      lens.push_back(static_cast<uint32_t>(a.size()));
+    }
+    return ugx_compile_words_ex(ptrs.data(), lens.data(), static_cast<uint32_t>(ptrs.size()), options, opc, cap, nop, pf);
+  }
+  catch (const std::bad_alloc&)
+  {
+    return UGX_E_NOMEM;
+  }
+}
