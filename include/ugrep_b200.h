@@ -196,7 +196,7 @@ int  ugx_compile_words_ex(const uint8_t *const *words, const uint32_t *lens, uin
  * reference's parser puts such a regex into the same tree DFA as a -F list (lib/pattern.cpp:286-311, 798-866), so this
  * is ugx_compile_words_ex on the alternatives.  Accepted: bytes other than the operators \ . [ ] ( ) { } * + ? | ^ $,
  * top-level `|`, a backslash before an operator or one of ! " # % & ' , - / : ; @ ` (that character), \t \f \v \a,
- * \Q...\E; with UGX_COMPILE_ICASE no byte >= 0x80 outside \Q...\E.  Anything else (classes, groups, repeats, anchors,
+ * \Q...\E, a leading (?i) (= UGX_COMPILE_ICASE); with UGX_COMPILE_ICASE no byte >= 0x80 outside \Q...\E.  Anything else (classes, groups, repeats, anchors,
  * \d \w \b \xHH ...) returns UGX_E_UNSUPPORTED: the regex compiler proper is not part of this library.  Alternative i (1-based) is accept index i. */
 int  ugx_compile_plain_regex(const uint8_t *regex, uint32_t len, uint32_t options, uint32_t *opc, uint32_t cap,
                              uint32_t *nop, ugx_prefilter *pf);

@@ -178,6 +178,11 @@ def test_plain_regex_alternations_compile_like_fixed_strings(tmp_path):
                 b"a\\x41", b"\\xe9", b"a]", b"a}", b"a\\", b"a\\~b", b"a\\<b", b"a\\eb", b"a\\_b"):
         with pytest.raises(api.UgxError):
             api.compile_plain([bad])
+    # a leading (?i) is the inline form of -i
+    O.ref_dump(["-e", "(?i)Bzaq|bxcd|Hello"], out)
+    pf, opc = parts(out)
+    got_opc, got_pf = api.compile_plain([b"(?i)Bzaq|bxcd|Hello"])
+    assert got_opc.tolist() == opc.tolist() and got_pf == pf
     with pytest.raises(api.UgxError):
         api.compile_plain(["naïve".encode()], icase=True)
     api.compile_plain(["\\Qnaïve\\E".encode()], icase=True)

@@ -659,7 +659,13 @@ extern "C" int ugx_compile_plain_regex(const uint8_t* regex, uint32_t len, uint3
   {
     std::vector<std::vector<uint8_t>> alts(1);
     bool quoted = false;
-    for (uint32_t i = 0; i < len; ++i)
+    uint32_t from = 0;
+    if (len >= 4 && memcmp(regex, "(?i)", 4) == 0) // the inline form of -i (lib/pattern.cpp:620-752)
+    {
+      options |= UGX_COMPILE_ICASE;
+      from = 4;
+    }
+    for (uint32_t i = from; i < len; ++i)
     {
       const uint8_t c = regex[i];
       if (quoted)
